@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the permanent hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun launches it for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on; fits one GPU):
+one step = ONE n=30 complex128 Gray-code Glynn permanent of a Haar-random 30x30 submatrix
+(tests/workloads.c4_matrix), all 2^29 Gray steps.  With N ranks the Gray range is cut into N
+contiguous slices (kernel K1 per rank) followed by one NCCL all-gather of 32-byte double-double
+partials and a fixed-order sum: strong scaling, value = permanents/s of the whole job.
+
+JSON keys beyond the base contract:
+  roofline      FP64-compute roofline of kernel K1 (this path is not HBM- or tensor-bound):
+                achieved = (8N-4)*2^(N-1) algorithmic flops / CUDA-event kernel time,
+                peak = DFMA probe measured on the same GPU in the same run (bp_fp64_peak).
+  cpu_baseline  the CPU oracle port (oracle/bossperm_oracle.c, double precision, all host threads)
+                on a bounded sample of the same workload.
+  e2e           the same metric through the public API with HOST buffers
+                (ShardedGlynnPermanent.compute: H2D of the matrix and D2H of the partials inside).
+  extra         secondary throughputs of the same path (other BASELINE configs), informational.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from tests import workloads  # noqa: E402
+
+N_PHOTONS = 30
+METRIC = "glynn_permanents_per_s_n30"
+UNIT = "permanents/s"
+ALG_FLOPS = (8 * N_PHOTONS - 4) * 2.0 ** (N_PHOTONS - 1)
+ISSUE_SLOTS = (6 * N_PHOTONS - 2) * 2.0 ** (N_PHOTONS - 1)    # FP64 instructions per permanent
+NOMINAL_FP64_TFLOPS = 37.0
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "C4: single n=30 complex128 Gray-code Glynn permanent, Haar(60, seed 30) 30x30 submatrix, 2^29 Gray steps",
+        "n": N_PHOTONS,
+        "terms_per_step": 2 ** (N_PHOTONS - 1),
+        "algorithmic_flops_per_step": ALG_FLOPS,
+        "sharding": f"Gray range split over {n_gpus} rank(s), all-gather of 32 B partials" if n_gpus > 1 else "single GPU",
+        "l2": "L2 flushed (256 MiB write) before every timed step; working set is 14.4 KB, path is FP64-compute-bound",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (ts, l) in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [l for (_, l) in self.lines]
+        for line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_sample(target_seconds=12.0):
+    """Times the CPU oracle port (double precision, all host threads) on a bounded sample of the C4
+    workload: the first 2^s of the 2^29 Gray steps of the same 30x30 matrix."""
+    from oracle import pyoracle as orc
+
+    A = workloads.c4_matrix(N_PHOTONS)
+    cores = os.cpu_count() or 1
+    lib = orc.lib()
+    import ctypes as C
+    out = np.zeros(2)
+    Aview = np.ascontiguousarray(A).view(np.float64)
+
+    def run(log2_terms):
+        # orc_glynn_gray_par_d on an N x N matrix covers 2^(N-1) steps; a range sample is taken by
+        # evaluating chunks of the full range in parallel threads over [0, 2^log2_terms).
+        T = 1 << log2_terms
+        nchunks = max(cores * 8, 8)
+        ranges = [(T * i // nchunks, T * (i + 1) // nchunks) for i in range(nchunks)]
+        res = [None] * nchunks
+
+        def work(idx):
+            o = np.zeros(2)
+            lib.orc_glynn_gray_range_d(Aview.ctypes.data_as(C.POINTER(C.c_double)), N_PHOTONS, ranges[idx][0], ranges[idx][1],
+                                       o.ctypes.data_as(C.POINTER(C.c_double)))
+            res[idx] = o
+        t0 = time.perf_counter()
+        nxt = iter(range(nchunks))
+        lock = threading.Lock()
+
+        def loop():
+            while True:
+                with lock:
+                    i = next(nxt, None)
+                if i is None:
+                    return
+                work(i)   # ctypes releases the GIL during the C call
+        ths = [threading.Thread(target=loop) for _ in range(cores)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        return time.perf_counter() - t0
+
+    del out
+    s = 20
+    t = run(s)
+    while t < 0.5 and s < N_PHOTONS - 1:
+        s += 2
+        t = run(s)
+    # scale to the target duration
+    grow = int(np.floor(np.log2(max(target_seconds / max(t, 1e-6), 1.0))))
+    s2 = min(N_PHOTONS - 1, s + grow)
+    if s2 > s:
+        t, s = run(s2), s2
+    frac = 2.0 ** (s - (N_PHOTONS - 1))
+    return {"value": frac / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first 2^{s} of 2^{N_PHOTONS - 1} Gray steps of the C4 n=30 matrix, oracle/bossperm_oracle.c double precision, "
+                      f"{cores} threads, {t:.2f} s; permanents/s extrapolated linearly in the step count",
+            "seconds": t}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
+    Python (~2.3 h per n=30 permanent) and /root/reference does not exist on the
+    GPU box, so the compiled restatement of its algorithm (the oracle port) is timed instead."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_sample(target_seconds=1.0)
+    vals, secs, last = [], [], None
+    budget = max(2.0, min(12.0, 60.0 / max(args.steps, 1)))
+    for _ in range(args.steps):
+        last = cpu_port_sample(target_seconds=budget)
+        vals.append(last["value"]); secs.append(last["seconds"])
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "ms_per_step is the time one full n=30 permanent would take on the host cores (extrapolated from the bounded sample)",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    from theboss_b200.distributed import ShardedGlynnPermanent
+
+    A = workloads.c4_matrix(N_PHOTONS)
+    job = ShardedGlynnPermanent(N_PHOTONS, device=local_rank)
+    job.upload(A)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        job.enqueue_resident()
+    result = job.finish()
+
+    # FP64 peak probe (roofline denominator), before the timed region so clocks are warm
+    fp64_peak = job.handle.fp64_peak(150.0)
+
+    # ---- device-timed leg: inputs resident in HBM ----------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = job.handle.launch_count()
+    barrier()
+    wall0 = time.time()
+    for k in range(args.steps):
+        flush.zero_()                       # L2 flush, outside the per-step event pair
+        starts[k].record()
+        job.enqueue_resident()
+        stops[k].record()
+    barrier()
+    wall1 = time.time()
+    launches = job.handle.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    result = job.finish()
+
+    # ---- kernel-only timing of K1 on this rank's slice (roofline) -------------------------------
+    kernel_ms = []
+    for _ in range(min(args.steps, 10)):
+        flush.zero_()
+        job.handle.timer_start()
+        job.handle.glynn_matrix_range_dev(job.d_A.data_ptr(), N_PHOTONS, job.lo, job.hi, job.d_part.data_ptr())
+        kernel_ms.append(job.handle.timer_stop())
+    k1_ms = statistics.mean(kernel_ms)
+    shard_flops = ALG_FLOPS * (job.hi - job.lo) / 2.0 ** (N_PHOTONS - 1)
+    achieved = shard_flops / (k1_ms * 1e-3) / 1e12
+
+    # ---- end-to-end leg: host buffers through the public API ------------------------------------
+    for _ in range(3):
+        job.compute(A)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        result_e2e = job.compute(A)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    assert result_e2e == result or abs(result_e2e - result) <= 1e-13 * abs(result)
+
+    if rank == 0:
+        # correctness gate on the timed result: long-double fixture of the same workload
+        with open(os.path.join(REPO, "tests", "golden", "large_permanents.json")) as f:
+            g = json.load(f)[f"glynn_n{N_PHOTONS}"]
+        rel = abs(result - complex(g["re"], g["im"])) / abs(complex(g["re"], g["im"]))
+        if rel > 1e-10:
+            raise SystemExit(f"bench.py: result {result} deviates from the long-double fixture by {rel:.3e}")
+        cpu = cpu_port_sample() if world == 1 else None
+        value = args.steps / (total_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": job.h2d_bytes,
+                    "d2h_bytes_per_step": job.d2h_bytes},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": None,
+                "kernel": "glynn_gray_kernel<30>", "kernel_ms": k1_ms,
+                "peak_source": "bp_fp64_peak DFMA probe on this GPU in this run (nominal B200 FP64: 37 TFLOP/s)",
+                "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+                "fp64_issue_slot_frac": (ISSUE_SLOTS * (job.hi - job.lo) / 2.0 ** (N_PHOTONS - 1)) * 2 / (k1_ms * 1e-3) / 1e12 / fp64_peak,
+                "structural_ceiling": (8 * N_PHOTONS - 4) / (12 * N_PHOTONS - 4),
+            },
+            "result": {"re": result.real, "im": result.imag, "rel_err_vs_long_double_fixture": rel},
+            "wall_s_timed_region": wall1 - wall0,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

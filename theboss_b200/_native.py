@@ -1,0 +1,242 @@
+"""ctypes binding of ``theboss_b200/lib/libbossperm.so`` (C ABI: include/bossperm.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing, or no sm_100 CUDA
+device is visible, every compute entry point raises ``BossPermError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbossperm.so")
+
+BP_MAX_N = 40
+BP_MAX_MODES = 256
+FORMULA_RYSER, FORMULA_CHIN_HUH, FORMULA_GLYNN = 0, 1, 2
+
+BP_OK, BP_ERR_INVALID, BP_ERR_SHAPE, BP_ERR_UNSUPPORTED, BP_ERR_CUDA, BP_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+
+
+class BossPermError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libbossperm error {code}: {message}")
+        self.code = code
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+# name -> (restype, argtypes); mirrors include/bossperm.h one to one.
+SIGNATURES = {
+    "bp_abi_version": (C.c_int, []),
+    "bp_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "bp_create_on_stream": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bp_destroy": (C.c_int, [C.c_void_p]),
+    "bp_last_error": (C.c_char_p, [C.c_void_p]),
+    "bp_synchronize": (C.c_int, [C.c_void_p]),
+    "bp_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bp_launch_count": (C.c_int64, [C.c_void_p]),
+    "bp_timer_start": (C.c_int, [C.c_void_p]),
+    "bp_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "bp_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, _dp]),
+    "bp_glynn_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp]),
+    "bp_glynn_matrix_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, _dp]),
+    "bp_glynn_matrix_range_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bp_glynn_single": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _dp]),
+    "bp_perm_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "bp_perm_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "bp_minors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bp_gccb_pmf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bp_gccb_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load libbossperm.so and attach the prototypes.  Raises if the library was not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise BossPermError(
+                    BP_ERR_CUDA,
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(make -C theboss_b200/csrc).  There is no CPU fallback.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def as_matrix(matrix) -> np.ndarray:
+    """ndarray or list of lists -> C-contiguous complex128 copy-if-needed (re-read on every call: the
+    reference lets callers mutate ``calculator.matrix`` in place,
+    tests/gcc_based_strategies_tests_base.py:89-92 in the reference)."""
+    a = np.ascontiguousarray(np.asarray(matrix, dtype=np.complex128))
+    if a.ndim != 2:
+        raise AttributeError
+    return a
+
+
+def as_state(state, m: Optional[int] = None) -> np.ndarray:
+    """list / tuple / ndarray of ints or integer-valued floats -> int32, zero-padded to m."""
+    a = np.asarray(state)
+    if a.ndim != 1:
+        a = a.reshape(-1)
+    out = np.zeros(len(a) if m is None else m, dtype=np.int32)
+    out[: len(a)] = a.astype(np.int64)
+    return out
+
+
+class Handle:
+    """One device + one stream + scratch (bp_handle).  Created lazily, never pickled."""
+
+    def __init__(self, device: int = 0, stream_ptr: Optional[int] = None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        if stream_ptr is None:
+            rc = self._lib.bp_create(int(device), C.byref(self._h))
+        else:
+            rc = self._lib.bp_create_on_stream(int(device), C.c_void_p(stream_ptr), C.byref(self._h))
+        if rc != BP_OK:
+            raise BossPermError(rc, self._lib.bp_last_error(None).decode())
+        self.device = int(device)
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != BP_OK:
+            msg = self._lib.bp_last_error(self._h).decode()
+            if rc == BP_ERR_SHAPE:
+                raise AttributeError(msg)   # bs_permanent_calculator_base.py:179-180
+            raise BossPermError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.bp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self._lib.bp_synchronize(self._h))
+
+    def device_info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.bp_device_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"sm_count": a.value, "cc": (b.value, c.value), "clock_khz": d.value}
+
+    def launch_count(self) -> int:
+        return int(self._lib.bp_launch_count(self._h))
+
+    def timer_start(self):
+        self._check(self._lib.bp_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.bp_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def fp64_peak(self, target_ms: float = 200.0) -> float:
+        tf = C.c_double()
+        self._check(self._lib.bp_fp64_peak(self._h, float(target_ms), C.byref(tf)))
+        return float(tf.value)
+
+    # -- K1 ----------------------------------------------------------------------------------
+    def glynn_matrix(self, A: np.ndarray) -> complex:
+        A = as_matrix(A)
+        if A.shape[0] != A.shape[1]:
+            raise AttributeError
+        out = (C.c_double * 2)()
+        self._check(self._lib.bp_glynn_matrix(self._h, A.ctypes.data, A.shape[0], out))
+        return complex(out[0], out[1])
+
+    def glynn_matrix_range(self, A: np.ndarray, lo: int, hi: int):
+        """Un-normalised double-double partial (re_hi, re_lo, im_hi, im_lo) over Gray steps [lo, hi)."""
+        A = as_matrix(A)
+        out = (C.c_double * 4)()
+        self._check(self._lib.bp_glynn_matrix_range(self._h, A.ctypes.data, A.shape[0], int(lo), int(hi), out))
+        return tuple(out)
+
+    def glynn_matrix_range_dev(self, dA_ptr: int, N: int, lo: int, hi: int, d_out_ptr: int):
+        self._check(self._lib.bp_glynn_matrix_range_dev(self._h, C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_ptr)))
+
+    def glynn_single(self, U: np.ndarray, s: np.ndarray, t: np.ndarray) -> complex:
+        out = (C.c_double * 2)()
+        self._check(self._lib.bp_glynn_single(self._h, U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, out))
+        return complex(out[0], out[1])
+
+    # -- K2 ----------------------------------------------------------------------------------
+    def perm_batched(self, U: np.ndarray, S: np.ndarray, T: np.ndarray, formula: int = FORMULA_GLYNN) -> np.ndarray:
+        U = as_matrix(U)
+        S = np.ascontiguousarray(S, dtype=np.uint8)
+        T = np.ascontiguousarray(T, dtype=np.uint8)
+        if S.shape != T.shape or S.ndim != 2 or S.shape[1] != U.shape[0]:
+            raise AttributeError
+        out = np.zeros(S.shape[0], dtype=np.complex128)
+        self._check(self._lib.bp_perm_batched(self._h, U.ctypes.data, U.shape[0], S.ctypes.data, T.ctypes.data,
+                                              S.shape[0], int(formula), out.ctypes.data))
+        return out
+
+    def perm_batched_dev(self, dU: int, m: int, dS: int, dT: int, B: int, formula: int, d_out: int):
+        self._check(self._lib.bp_perm_batched_dev(self._h, C.c_void_p(dU), int(m), C.c_void_p(dS), C.c_void_p(dT),
+                                                  int(B), int(formula), C.c_void_p(d_out)))
+
+    # -- K3 ----------------------------------------------------------------------------------
+    def minors(self, U: np.ndarray, s: np.ndarray, t: np.ndarray, formula: int = FORMULA_CHIN_HUH) -> np.ndarray:
+        out = np.zeros(U.shape[0], dtype=np.complex128)
+        self._check(self._lib.bp_minors(self._h, U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, int(formula),
+                                        out.ctypes.data))
+        return out
+
+    def gccb_pmf(self, U: np.ndarray, s: np.ndarray, t: np.ndarray, want_minors: bool = False):
+        m = U.shape[0]
+        pmf = np.zeros(m, dtype=np.float64)
+        minors = np.zeros(m, dtype=np.complex128) if want_minors else None
+        self._check(self._lib.bp_gccb_pmf(self._h, U.ctypes.data, m, s.ctypes.data, t.ctypes.data, pmf.ctypes.data,
+                                          minors.ctypes.data if want_minors else None))
+        return (pmf, minors) if want_minors else pmf
+
+    # -- K3 + K4 -----------------------------------------------------------------------------
+    def gccb_simulate(self, U: np.ndarray, s: np.ndarray, n_samples: int, eta: float = -1.0, seed: int = 0,
+                      first_sample: int = 0, tape: Optional[np.ndarray] = None) -> np.ndarray:
+        m = U.shape[0]
+        out = np.zeros((int(n_samples), m), dtype=np.int32)
+        tp = None
+        if tape is not None:
+            tape = np.ascontiguousarray(tape, dtype=np.float64)
+            n = int(s.sum())
+            if tape.shape != (int(n_samples), 1 + 2 * n):
+                raise ValueError(f"decision tape must have shape ({n_samples}, {1 + 2 * n})")
+            tp = tape.ctypes.data
+        self._check(self._lib.bp_gccb_simulate(self._h, U.ctypes.data, m, s.ctypes.data, int(n_samples), float(eta),
+                                               int(seed) & (2 ** 64 - 1), int(first_sample), tp, out.ctypes.data))
+        return out
+
+
+_default_handles = {}
+_default_lock = threading.Lock()
+
+
+def default_handle(device: int = 0) -> Handle:
+    """Process-wide handle per device, created on first use (after fork/spawn/unpickle too)."""
+    key = (os.getpid(), int(device))
+    with _default_lock:
+        h = _default_handles.get(key)
+        if h is None:
+            h = Handle(device)
+            _default_handles[key] = h
+        return h

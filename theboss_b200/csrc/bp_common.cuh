@@ -1,0 +1,129 @@
+// bp_common.cuh -- shared device helpers and the host-side context of libbossperm.so (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bossperm.h"
+
+// ---------------------------------------------------------------------------------------------
+// host context
+// ---------------------------------------------------------------------------------------------
+struct bp_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0, clock_khz = 0;
+    int64_t launches = 0;
+    // device scratch (grown on demand, never shrunk)
+    void *d_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t d_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // pinned host staging
+    void *h_pin = nullptr;
+    size_t h_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    char err[512] = {0};
+};
+
+int bp_fail(bp_context *h, int code, const char *fmt, ...);
+int bp_reserve(bp_context *h, int slot, size_t bytes);   // device scratch slot
+int bp_reserve_pinned(bp_context *h, size_t bytes);
+
+#define BP_CUDA(h, call)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return bp_fail((h), BP_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                 \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define BP_CHECK_LAUNCH(h)                                                                   \
+    do {                                                                                     \
+        (h)->launches++;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess)                                                               \
+            return bp_fail((h), BP_ERR_CUDA, "kernel launch failed: %s (%s:%d)",             \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+    } while (0)
+
+// scratch slot assignment
+enum { BP_SLOT_MATRIX = 0, BP_SLOT_PARTIALS = 1, BP_SLOT_OUT = 2, BP_SLOT_STATE = 3, BP_SLOT_ITEMS = 4,
+       BP_SLOT_AUX = 5, BP_SLOT_TAPE = 6, BP_SLOT_MISC = 7 };
+
+// ---------------------------------------------------------------------------------------------
+// device helpers: complex, double-double
+// ---------------------------------------------------------------------------------------------
+struct cplx {
+    double re, im;
+};
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    cplx r;
+    r.re = a.re * b.re - a.im * b.im;   // DMUL + DFMA
+    r.im = a.re * b.im + a.im * b.re;   // DMUL + DFMA
+    return r;
+}
+
+// error-free transformations (Knuth TwoSum / Dekker FastTwoSum); no multiplications, so FMA
+// contraction cannot alter them.
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    double bb = __dsub_rn(s, a);
+    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+}
+__device__ __forceinline__ void fast_two_sum(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    e = __dsub_rn(b, __dsub_rn(s, a));
+}
+
+struct dd {
+    double hi, lo;
+};
+__device__ __forceinline__ dd dd_add_d(dd x, double y) {
+    double s, e;
+    two_sum(x.hi, y, s, e);
+    e = __dadd_rn(e, x.lo);
+    dd r;
+    fast_two_sum(s, e, r.hi, r.lo);
+    return r;
+}
+__device__ __forceinline__ dd dd_add(dd x, dd y) {
+    double s, e;
+    two_sum(x.hi, y.hi, s, e);
+    e = __dadd_rn(e, __dadd_rn(x.lo, y.lo));
+    dd r;
+    fast_two_sum(s, e, r.hi, r.lo);
+    return r;
+}
+__device__ __forceinline__ dd dd_shfl_down(dd x, int delta) {
+    dd r;
+    r.hi = __shfl_down_sync(0xffffffffu, x.hi, delta);
+    r.lo = __shfl_down_sync(0xffffffffu, x.lo, delta);
+    return r;
+}
+
+// Block-wide double-double complex reduction.  Result valid in thread 0.  `red` needs
+// 4 * (blockDim.x / 32) doubles of shared memory.
+__device__ __forceinline__ void block_reduce_dd(dd &re, dd &im, double *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        re = dd_add(re, dd_shfl_down(re, d));
+        im = dd_add(im, dd_shfl_down(im, d));
+    }
+    if (lane == 0) {
+        red[4 * warp + 0] = re.hi; red[4 * warp + 1] = re.lo;
+        red[4 * warp + 2] = im.hi; red[4 * warp + 3] = im.lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dd r = {red[0], red[1]}, i = {red[2], red[3]};
+        for (int w = 1; w < nw; ++w) {   // fixed order
+            dd a = {red[4 * w + 0], red[4 * w + 1]}, b = {red[4 * w + 2], red[4 * w + 3]};
+            r = dd_add(r, a);
+            i = dd_add(i, b);
+        }
+        re = r; im = i;
+    }
+}

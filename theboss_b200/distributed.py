@@ -1,0 +1,112 @@
+"""Multi-GPU sharding of the permanent hot path (one process per GPU, torch.distributed / NCCL).
+
+The reference has no distributed backend; what shards is
+
+* one large Glynn permanent: the 2^(N-1) Gray steps are split into ``world_size`` contiguous
+  slices, every rank runs kernel K1 on its slice and produces ONE double-double complex partial
+  (32 bytes); a single all-gather follows and every rank adds the partials in rank order, so the
+  result is identical on all ranks and independent of NCCL's algorithm choice;
+* batches of independent samples / items: contiguous slices per rank, no traffic until the final
+  gather (``shard_bounds``).
+
+torch is used for plumbing only (device buffers, streams, the collective).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def shard_bounds(total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of ``total`` units owned by ``rank`` (sizes differ by at most 1)."""
+    q, r = divmod(int(total), int(world_size))
+    lo = q * rank + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def gray_shard(N: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Slice of the 2^(N-1) Gray steps of an N x N Glynn permanent owned by ``rank``."""
+    return shard_bounds(1 << (N - 1), world_size, rank)
+
+
+def combine_partials(partials: np.ndarray, N: int) -> complex:
+    """Fixed-order (rank order) sum of double-double partials {re_hi, re_lo, im_hi, im_lo}, scaled by
+    2^-(N-1) (glynn_gray_permanent_calculator.py:69 in the reference).  Python floats: TwoSum in
+    plain IEEE double arithmetic, so every rank gets the same bits."""
+    def two_sum(a, b):
+        s = a + b
+        bb = s - a
+        return s, (a - (s - bb)) + (b - bb)
+
+    acc = [[0.0, 0.0], [0.0, 0.0]]
+    for p in np.asarray(partials, dtype=np.float64).reshape(-1, 4):
+        for c in range(2):
+            s, e = two_sum(acc[c][0], float(p[2 * c]))
+            e += acc[c][1] + float(p[2 * c + 1])
+            hi = s + e
+            acc[c] = [hi, e - (hi - s)]
+    scale = 2.0 ** (-(N - 1))
+    return complex((acc[0][0] + acc[0][1]) * scale, (acc[1][0] + acc[1][1]) * scale)
+
+
+class ShardedGlynnPermanent:
+    """perm(A) of one explicit N x N matrix over all ranks of a process group.
+
+    ``compute(A)`` takes a HOST matrix (the user-facing call: upload, K1 on this rank's Gray slice,
+    all-gather of 32-byte partials, fixed-order sum); ``enqueue_resident()`` / ``finish()`` is the same
+    with the matrix already resident in HBM (bench.py's device-timed leg)."""
+
+    def __init__(self, N: int, device: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _native
+
+        self._torch, self._dist, self.group = torch, dist, group
+        self.N = int(N)
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.world_size = dist.get_world_size(group) if self.distributed else 1
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.lo, self.hi = gray_shard(self.N, self.world_size, self.rank)
+        stream = torch.cuda.current_stream(self.device)
+        self.handle = _native.Handle(self.device, stream_ptr=stream.cuda_stream)
+        dev = torch.device("cuda", self.device)
+        self.d_A = torch.zeros(self.N * self.N * 2, dtype=torch.float64, device=dev)
+        self.d_part = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.d_all = torch.zeros(4 * self.world_size, dtype=torch.float64, device=dev)
+        self.h_A = torch.zeros(self.N * self.N * 2, dtype=torch.float64).pin_memory()
+        self.h_all = torch.zeros(4 * self.world_size, dtype=torch.float64).pin_memory()
+
+    def upload(self, A: np.ndarray) -> None:
+        A = np.ascontiguousarray(A, dtype=np.complex128)
+        assert A.shape == (self.N, self.N)
+        self.h_A.numpy()[:] = A.view(np.float64).reshape(-1)
+        self.d_A.copy_(self.h_A, non_blocking=True)
+
+    def enqueue_resident(self) -> None:
+        """K1 on this rank's slice + the partial exchange, all on the current stream, no host sync."""
+        self.handle.glynn_matrix_range_dev(self.d_A.data_ptr(), self.N, self.lo, self.hi, self.d_part.data_ptr())
+        if self.world_size > 1:
+            self._dist.all_gather_into_tensor(self.d_all, self.d_part, group=self.group)
+        else:
+            self.d_all.copy_(self.d_part)
+
+    def finish(self) -> complex:
+        self.h_all.copy_(self.d_all, non_blocking=True)
+        self._torch.cuda.current_stream(self.device).synchronize()
+        return combine_partials(self.h_all.numpy(), self.N)
+
+    def compute(self, A: np.ndarray) -> complex:
+        self.upload(A)
+        self.enqueue_resident()
+        return self.finish()
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.N * self.N * 16
+
+    @property
+    def d2h_bytes(self) -> int:
+        return 32 * self.world_size
