@@ -1,0 +1,113 @@
+"""K3 parity (GPU): all one-particle-removed permanents + the GCC-B step pmf, vs the reference golden
+vectors (tests/test_bs_submatrices_permanent_calculators.py cases) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import workloads
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from theboss_b200 import _native
+    return _native.default_handle(0)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def _occ(rng, m, n):
+    out = np.zeros(m, dtype=np.int32)
+    for j in rng.randint(0, m, n):
+        out[j] += 1
+    return out
+
+
+def test_submatrices_classes_against_reference_golden(golden_dir):
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.bs_cc_ch_submatrices_permanent_calculator import (
+        BSCCCHSubmatricesPermanentCalculator)
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.bs_cc_ryser_submatrices_permanent_calculator import (
+        BSCCRyserSubmatricesPermanentCalculator)
+    z = np.load(os.path.join(golden_dir, "submatrices_permanents.npz"))
+    for i in range(int(z["n_cases"])):
+        U, s, t = z[f"U_{i}"], z[f"s_{i}"], z[f"t_{i}"]
+        ref = z[f"chin_huh_{i}"]
+        scale = max(np.abs(ref).max(), 1e-30)
+        for cls in (BSCCCHSubmatricesPermanentCalculator, BSCCRyserSubmatricesPermanentCalculator):
+            got = cls(U, s, t).compute_permanents()
+            assert isinstance(got, list) and len(got) == len(s) and isinstance(got[0], np.complex128)
+            assert np.abs(np.array(got) - ref).max() <= REL_TOL * scale, (i, cls.__name__)
+            assert np.abs(np.array(got) - z[f"ryser_{i}"]).max() <= 1e-8 * scale
+
+
+@pytest.mark.parametrize("m,k", [(4, 2), (5, 3), (8, 6), (12, 7), (12, 10), (16, 13), (20, 14), (24, 16), (28, 17)])
+def test_minors_random_occupations_vs_oracle(handle, orc, m, k):
+    rng = np.random.RandomState(31 * m + k)
+    U = workloads.haar(m, 3 * m + k)
+    for rep in range(4):
+        s = np.array([1] * k + [0] * (m - k), dtype=np.int32) if rep == 0 else _occ(rng, m, k)
+        t = _occ(rng, m, k - 1)
+        if rep == 3:
+            t[:] = 0
+            t[rng.choice(m, k - 1, replace=False)] = 1   # collision-free outputs: the full 2^(k-2) walk
+        got = handle.minors(U, s, t)
+        want = orc.submatrices(U, s, t, orc.RYSER, "ld")
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= REL_TOL * scale, (rep, s, t)
+        assert np.all(got[s == 0] == 0)
+
+
+@pytest.mark.parametrize("k,collision_free", [(20, False), (20, True), (24, False)])
+def test_minors_headline_sizes(handle, orc, k, collision_free):
+    """BASELINE config 3 shape: m = 2k, collision-free input, k-1 outputs placed at random."""
+    U, s, t = workloads.c3_step(k, 2 * k, collision_free)
+    got = handle.minors(U, s, t)
+    want = orc.submatrices(U, s, t, orc.RYSER, "ld")   # 80-bit: Ryser-form error ~1e-13 here
+    assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max()
+
+
+def test_minors_equal_single_permanents_with_one_particle_removed(handle):
+    """The property the reference tests (tests/test_bs_submatrices_permanent_calculators.py:75-109), as full
+    complex numbers, against this package's own single-permanent kernel."""
+    rng = np.random.RandomState(8)
+    m, k = 10, 8
+    U = workloads.haar(m, 11)
+    s, t = _occ(rng, m, k), _occ(rng, m, k - 1)
+    minors = handle.minors(U, s, t)
+    idx = np.nonzero(s)[0]
+    S = np.repeat(s[None, :], len(idx), axis=0).astype(np.uint8)
+    S[np.arange(len(idx)), idx] -= 1
+    T = np.repeat(t[None, :], len(idx), axis=0).astype(np.uint8)
+    singles = handle.perm_batched(U, S, T)
+    assert np.abs(minors[idx] - singles).max() <= 1e-13 * np.abs(singles).max()
+
+
+def test_k_equals_one_edge_case(handle):
+    U = workloads.haar(5, 2)
+    s = np.array([0, 0, 1, 0, 0], dtype=np.int32)
+    got = handle.minors(U, s, np.zeros(5, dtype=np.int32))
+    assert np.array_equal(got, s.astype(np.complex128))   # bs_submatrices_permanent_calculator_base.py:157-158
+
+
+@pytest.mark.parametrize("m,k", [(6, 1), (6, 2), (6, 4), (10, 7), (16, 11), (30, 15)])
+def test_step_pmf_vs_oracle(handle, orc, m, k):
+    rng = np.random.RandomState(m + k)
+    U = workloads.haar(m, m * k)
+    s, t = _occ(rng, m, k), _occ(rng, m, k - 1)
+    pmf, minors = handle.gccb_pmf(U, s, t, want_minors=True)
+    want = orc.gccb_pmf(U, s, t, "ld")
+    assert abs(pmf.sum() - 1) <= 1e-14
+    assert np.abs(pmf - want).max() <= 1e-12
+
+
+def test_shape_error(handle):
+    U = workloads.haar(4, 1)
+    with pytest.raises(AttributeError):
+        handle.minors(U, np.array([1, 1, 0, 0], dtype=np.int32), np.array([1, 1, 0, 0], dtype=np.int32))

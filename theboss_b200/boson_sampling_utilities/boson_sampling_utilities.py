@@ -1,0 +1,52 @@
+"""Host-side helpers of the permanent path (NumPy), mirroring the three functions of the reference's
+``theboss/boson_sampling_utilities/boson_sampling_utilities.py`` that the hot path touches:
+
+* ``mode_occupation_to_mode_assignment``                 (:61-78)
+* ``prepare_interferometer_matrix_in_expanded_space``    (:287-342, helper :263-284)
+* ``EffectiveScatteringMatrixCalculator``                (:545-626)
+
+The expansion of rows/columns by occupation is done on the device inside the kernels
+(theboss_b200/csrc/util_kernels.cu, guan_kernel.cu); the class below exists for API compatibility and
+for callers that want the explicit matrix.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def mode_occupation_to_mode_assignment(mode_occupation: Sequence[int]) -> Tuple[int, ...]:
+    """2nd-quantisation occupation -> 1st-quantisation list of modes, e.g. [2,0,1] -> (0,0,2)."""
+    occ = np.asarray(mode_occupation).astype(np.int64)
+    return tuple(int(v) for v in np.repeat(np.arange(len(occ)), occ))
+
+
+def prepare_interferometer_matrix_in_expanded_space(interferometer_matrix) -> np.ndarray:
+    """m x m (possibly lossy) matrix -> 2m x 2m dilation (an isometry on the m physical input modes, which
+    is all the samplers use): with the SVD ``V diag(sv) W`` the result is ``blockdiag(V, I) @ [[diag(sv), L], [L, diag(sv)]] @ blockdiag(W, I)`` where
+    ``L = diag(sqrt(max(0, 1 - sv^2)))`` moves lost particles into the m extra modes."""
+    A = np.asarray(interferometer_matrix, dtype=np.complex128)
+    m = A.shape[0]
+    V, sv, W = np.linalg.svd(A)
+    eye, zero = np.eye(m), np.zeros((m, m), dtype=V.dtype)
+    loss = np.sqrt(np.clip(1.0 - np.array([x ** 2 for x in sv]), 0.0, None))
+    core = np.block([[np.diag(sv), np.diag(loss)], [np.diag(loss), np.diag(sv)]])
+    return np.block([[V, zero], [zero, eye]]) @ core @ np.block([[W, zero], [zero, eye]])
+
+
+class EffectiveScatteringMatrixCalculator:
+    """Rows of ``matrix`` repeated by the output occupation, columns by the input occupation;
+    ``[]`` when either side is empty (reference :606-607)."""
+
+    def __init__(self, matrix, input_state: Optional[Sequence[int]] = None,
+                 output_state: Optional[Sequence[int]] = None) -> None:
+        self.matrix = matrix
+        self.input_state = [] if input_state is None else input_state
+        self.output_state = [] if output_state is None else output_state
+
+    def calculate(self) -> List[np.ndarray]:
+        if sum(self.input_state) == 0 or sum(self.output_state) == 0:
+            return []
+        U = np.asarray(self.matrix, dtype=np.complex128)
+        cols = list(mode_occupation_to_mode_assignment(self.input_state))
+        rows = list(mode_occupation_to_mode_assignment(self.output_state))
+        return list(U[np.ix_(rows, cols)])

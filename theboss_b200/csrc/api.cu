@@ -12,6 +12,11 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
 int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int32_t *d_s, const int32_t *d_t,
                                int N, double *dA);
 int bp_fp64_peak_launch(bp_context *h, int iters, double *d_sink);
+int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
+                 long long B, double *d_out);
+#define BP_HAVE_K2 1
+#define BP_HAVE_K3 1
+#define BP_HAVE_K4 1
 
 static char g_global_err[512] = "no error";
 
@@ -269,6 +274,49 @@ int bp_glynn_single(bp_handle h, const double *U, int m, const int32_t *s, const
     const double scale = ldexp(1.0, -(N - 1));
     out[0] = (res[0] + res[1]) * scale;
     out[1] = (res[2] + res[3]) * scale;
+    return BP_OK;
+}
+
+
+// ---- K2 --------------------------------------------------------------------------------------
+int bp_perm_batched_dev(bp_handle h, const double *dU, int m, const uint8_t *dS, const uint8_t *dT, int64_t B,
+                        int formula, double *d_out) {
+    if (!h || !dU || !dS || !dT || !d_out) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: NULL argument");
+    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched_dev: m=%d outside [1, %d]", m, BP_MAX_MODES);
+    if (formula < BP_FORMULA_RYSER || formula > BP_FORMULA_GLYNN) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: formula %d", formula);
+    if (B < 0) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: B=%lld", (long long)B);
+    BP_CUDA(h, cudaSetDevice(h->device));
+    return bp_k2_launch(h, dU, m, dS, dT, (long long)B, d_out);
+}
+
+int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const uint8_t *T, int64_t B, int formula,
+                    double *out) {
+    if (!h || !U || !S || !T || !out) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched: NULL argument");
+    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: m=%d outside [1, %d]", m, BP_MAX_MODES);
+    if (formula < BP_FORMULA_RYSER || formula > BP_FORMULA_GLYNN) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched: formula %d", formula);
+    if (B < 0) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched: B=%lld", (long long)B);
+    if (B == 0) return BP_OK;
+    for (int64_t b = 0; b < B; ++b) {   // the reference raises before computing (bs_permanent_calculator_base.py:179-180)
+        long ns = 0, nt = 0;
+        for (int v = 0; v < m; ++v) { ns += S[b * m + v]; nt += T[b * m + v]; }
+        if (ns != nt) return bp_fail(h, BP_ERR_SHAPE, "bp_perm_batched: item %lld has %ld input vs %ld output particles", (long long)b, ns, nt);
+        if (ns > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: item %lld has n=%ld > %d", (long long)b, ns, BP_MAX_N);
+    }
+    BP_CUDA(h, cudaSetDevice(h->device));
+    const size_t ub = sizeof(double) * 2 * (size_t)m * m, sb = (size_t)B * m, ob = sizeof(double) * 2 * (size_t)B;
+    int rc;
+    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_STATE, 2 * sb + 32))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_OUT, ob))) return rc;
+    // U, S, T are read by the DMA engine straight from the caller's (pageable) buffers
+    BP_CUDA(h, cudaMemcpyAsync(h->d_buf[BP_SLOT_AUX], U, ub, cudaMemcpyHostToDevice, h->stream));
+    unsigned char *dS = (unsigned char *)h->d_buf[BP_SLOT_STATE], *dT = dS + ((sb + 15) / 16) * 16;
+    BP_CUDA(h, cudaMemcpyAsync(dS, S, sb, cudaMemcpyHostToDevice, h->stream));
+    BP_CUDA(h, cudaMemcpyAsync(dT, T, sb, cudaMemcpyHostToDevice, h->stream));
+    rc = bp_k2_launch(h, (const double *)h->d_buf[BP_SLOT_AUX], m, dS, dT, (long long)B, (double *)h->d_buf[BP_SLOT_OUT]);
+    if (rc) return rc;
+    BP_CUDA(h, cudaMemcpyAsync(out, h->d_buf[BP_SLOT_OUT], ob, cudaMemcpyDeviceToHost, h->stream));
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
     return BP_OK;
 }
 

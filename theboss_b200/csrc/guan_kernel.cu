@@ -1,0 +1,253 @@
+// guan_kernel.cu -- K2: batched single permanents with input/output multiplicities.
+//
+// Replaces B calls of compute_permanent() of the Guan-code calculators
+// (reference: theboss/boson_sampling_utilities/permanent_calculators/
+//  bs_permanent_calculator_base.py:166-209, chin_huh_permanent_calculator.py:38-59,
+//  ryser_permanent_calculator.py:45-64; also glynn_gray_permanent_calculator.py:41-71, which
+//  evaluates the same quantity on the expanded matrix) that share one interferometer U.
+//
+// Chin-Huh form, generalised Gray (Guan) walk over the side with FEWER terms (perm A = perm A^T):
+//   perm = 2^-n sum_r (-1)^{sum r} prod_v C(w_v, r_v) prod_{j=1..n} ( sum_v (w_v - 2 r_v) X[v][j] )
+// with the product side expanded to its n particles (columns repeated by multiplicity), and the
+// r <-> w - r symmetry halving the walk (guan_walker.cuh).
+//
+// Scheduling: one thread block per item; a counting sort orders items by (n, descending cost) so
+// that one templated launch per distinct n runs longest-first (LPT) over the 148 SMs.
+#include "bp_common.cuh"
+#include "guan_walker.cuh"
+
+struct K2Meta {            // per item, written by k2_prep_kernel
+    int n;                 // particles (-1: sum(s) != sum(t))
+    int walk_outputs;      // 1: walk over output modes (rows), 0: over input modes (columns)
+    float log2cost;
+};
+
+// ---------------------------------------------------------------------------------------------
+// prep: per item particle numbers, walk side, cost
+// ---------------------------------------------------------------------------------------------
+__global__ void k2_prep_kernel(const unsigned char *__restrict__ S, const unsigned char *__restrict__ T, int m,
+                               long long B, K2Meta *__restrict__ meta, int *__restrict__ bins /*[41*64]*/) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const unsigned char *s = S + b * m, *t = T + b * m;
+    int ns = 0, nt = 0;
+    for (int v = 0; v < m; ++v) { ns += s[v]; nt += t[v]; }
+    K2Meta me;
+    if (ns != nt || ns > BP_MAX_N) { me.n = -1; me.walk_outputs = 0; me.log2cost = 0.f; meta[b] = me; return; }
+    const double cs = guan_terms_of(s, m), ct = guan_terms_of(t, m);
+    me.n = ns;
+    me.walk_outputs = (ct < cs) ? 1 : 0;
+    me.log2cost = (float)log2(ct < cs ? ct : cs);
+    meta[b] = me;
+    int bucket = (int)me.log2cost;
+    if (bucket > 63) bucket = 63;
+    atomicAdd(&bins[ns * 64 + (63 - bucket)], 1);   // descending cost inside each n
+}
+
+// exclusive scan of the 41*64 bins (one block) + per-n offsets
+__global__ void k2_scan_kernel(int *__restrict__ bins, int *__restrict__ n_offsets /*[42]*/) {
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int n = 0; n <= BP_MAX_N; ++n) {
+            n_offsets[n] = run;
+            for (int c = 0; c < 64; ++c) { const int v = bins[n * 64 + c]; bins[n * 64 + c] = run; run += v; }
+        }
+        n_offsets[BP_MAX_N + 1] = run;
+    }
+}
+
+__global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, int *__restrict__ bins,
+                                  int *__restrict__ order, double *__restrict__ out) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const K2Meta me = meta[b];
+    if (me.n < 0) {   // shape error: the host API refuses earlier; the _dev API marks the item
+        out[2 * b] = __longlong_as_double(0x7ff8000000000000ll); out[2 * b + 1] = out[2 * b];
+        return;
+    }
+    int bucket = (int)me.log2cost;
+    if (bucket > 63) bucket = 63;
+    const int pos = atomicAdd(&bins[me.n * 64 + (63 - bucket)], 1);
+    order[pos] = (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct K2Cfg {
+    static constexpr int MINB = (N <= 4) ? 6 : (N <= 16) ? 4 : (N <= 26) ? 3 : 2;
+};
+
+template <int N>
+__device__ __forceinline__ void k2_product(const double (&sr)[N], const double (&si)[N], double &pr, double &pi) {
+    constexpr int NCH = (N >= 9) ? 3 : (N >= 4 ? 2 : 1);
+    cplx p[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { p[c].re = sr[c]; p[c].im = si[c]; }
+#pragma unroll
+    for (int j = NCH; j < N; ++j) {
+        cplx s = {sr[j], si[j]};
+        p[j % NCH] = cmul(p[j % NCH], s);
+    }
+    cplx r = p[0];
+#pragma unroll
+    for (int c = 1; c < NCH; ++c) r = cmul(r, p[c]);
+    pr = r.re; pi = r.im;
+}
+
+template <int N>
+__global__ void __launch_bounds__(GW_THREADS, K2Cfg<N>::MINB)
+k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ S,
+               const unsigned char *__restrict__ T, const K2Meta *__restrict__ meta,
+               const int *__restrict__ order, int first, double *__restrict__ out) {
+    __shared__ GuanItem item;
+    __shared__ short col_mode[N];
+    __shared__ double2 X2[N * N];                       // 2 * X[v][j], D <= N rows
+    __shared__ unsigned char rdig[N * GW_THREADS];      // per-thread digit vectors (column = thread)
+    __shared__ double red[4 * (GW_THREADS / 32)];
+
+    const int b = order[first + blockIdx.x];
+    const K2Meta me = meta[b];
+    const unsigned char *walk = (me.walk_outputs ? T : S) + (long long)b * m;
+    const unsigned char *prod = (me.walk_outputs ? S : T) + (long long)b * m;
+    if (threadIdx.x == 0) {
+        guan_item_build(item, walk, m);
+        int c = 0;
+        for (int v = 0; v < m; ++v)
+            for (int a = 0; a < prod[v] && c < N; ++a) col_mode[c++] = (short)v;
+    }
+    __syncthreads();
+    const int D = item.D;
+    const double2 *U2 = reinterpret_cast<const double2 *>(U);
+    for (int e = threadIdx.x; e < D * N; e += GW_THREADS) {
+        const int v = e / N, j = e - v * N;
+        const int wm = item.mode[v], pm = col_mode[j];
+        // U[out_mode][in_mode]: walking outputs -> rows of U, walking inputs -> columns of U
+        const double2 u = me.walk_outputs ? U2[wm * m + pm] : U2[pm * m + wm];
+        X2[e] = make_double2(2.0 * u.x, 2.0 * u.y);
+    }
+    __syncthreads();
+
+    const unsigned long long total = item.terms;
+    unsigned long long span = (total + GW_THREADS - 1) / GW_THREADS;
+    if (span < 1) span = 1;
+    const unsigned long long start = (unsigned long long)threadIdx.x * span;
+    dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
+
+    if (start < total) {
+        const unsigned long long end = (total - start < span) ? total : start + span;
+        unsigned char *r = rdig + threadIdx.x;
+        GuanState st;
+        guan_seek(item, start, r, st);
+        double sr[N], si[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+#pragma unroll 1
+        for (int v = 0; v < D; ++v) {
+            const double c = 0.5 * (double)((int)item.mult[v] - 2 * (int)r[v * GW_THREADS]);
+            const double2 *row = X2 + v * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 a = row[j];
+                sr[j] = fma(c, a.x, sr[j]);
+                si[j] = fma(c, a.y, si[j]);
+            }
+        }
+        double pr, pi;
+        k2_product<N>(sr, si, pr, pi);
+        double w = (start & 1ull) ? -st.binom : st.binom;
+        double wr = w * pr, wi = w * pi;
+        unsigned cnt = 0;
+#pragma unroll 1
+        for (unsigned long long I = start + 1; I < end; ++I) {
+            if (++cnt == 64u) {
+                cnt = 0;
+                acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+                wr = 0.0; wi = 0.0;
+            }
+            int delta;
+            const int v = guan_step(item, r, st, delta);
+            const double sg = (delta > 0) ? -1.0 : 1.0;       // sums -= 2 * delta * X[v]
+            const double2 *row = X2 + v * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 a = row[j];
+                sr[j] = fma(sg, a.x, sr[j]);
+                si[j] = fma(sg, a.y, si[j]);
+            }
+            k2_product<N>(sr, si, pr, pi);
+            w = (I & 1ull) ? -st.binom : st.binom;
+            wr = fma(w, pr, wr);
+            wi = fma(w, pi, wi);
+        }
+        acc_re = dd_add_d(acc_re, wr);
+        acc_im = dd_add_d(acc_im, wi);
+    }
+    block_reduce_dd(acc_re, acc_im, red);
+    if (threadIdx.x == 0) {
+        const double scale = ldexp(1.0, -N);                  // 2^-n (chin_huh_permanent_calculator.py:41)
+        out[2 * (long long)b] = (acc_re.hi + acc_re.lo) * scale;
+        out[2 * (long long)b + 1] = (acc_im.hi + acc_im.lo) * scale;
+    }
+}
+
+// items without particles: permanent of the empty matrix = 1
+__global__ void k2_empty_kernel(const int *__restrict__ order, int first, int count, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long b = order[first + i];
+    out[2 * b] = 1.0; out[2 * b + 1] = 0.0;
+}
+
+typedef void (*k2_fn)(const double *, int, const unsigned char *, const unsigned char *, const K2Meta *, const int *, int, double *);
+template <int N>
+static void k2_entry(k2_fn *fn) {
+    fn[N] = k2_perm_kernel<N>;
+    if constexpr (N > 1) k2_entry<N - 1>(fn);
+}
+static k2_fn g_k2_fn[BP_MAX_N + 1];
+static bool g_k2_init = false;
+
+// All pointers are device pointers.  Enqueues prep + sort + one launch per distinct n; needs one
+// small D2H copy (per-n offsets) in the middle, so it synchronises the stream once.
+int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
+                 long long B, double *d_out) {
+    if (!g_k2_init) { k2_entry<BP_MAX_N>(g_k2_fn); g_k2_init = true; }
+    if (B <= 0) return BP_OK;
+    if (B > 0x7fffffffll) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: B=%lld items exceeds 2^31-1", B);
+    const size_t meta_bytes = sizeof(K2Meta) * (size_t)B, order_bytes = sizeof(int) * (size_t)B;
+    const size_t bins_bytes = sizeof(int) * ((BP_MAX_N + 1) * 64 + BP_MAX_N + 2);
+    int rc = bp_reserve(h, BP_SLOT_ITEMS, meta_bytes + order_bytes + bins_bytes + 64);
+    if (rc) return rc;
+    if ((rc = bp_reserve_pinned(h, 4096))) return rc;
+    char *base = (char *)h->d_buf[BP_SLOT_ITEMS];
+    K2Meta *meta = (K2Meta *)base;
+    int *order = (int *)(base + ((meta_bytes + 15) / 16) * 16);
+    int *bins = (int *)((char *)order + ((order_bytes + 15) / 16) * 16);
+    int *n_offsets = bins + (BP_MAX_N + 1) * 64;
+    BP_CUDA(h, cudaMemsetAsync(bins, 0, bins_bytes, h->stream));
+    const int tb = 256, gb = (int)((B + tb - 1) / tb);
+    k2_prep_kernel<<<gb, tb, 0, h->stream>>>(dS, dT, m, B, meta, bins);
+    BP_CHECK_LAUNCH(h);
+    k2_scan_kernel<<<1, 32, 0, h->stream>>>(bins, n_offsets);
+    BP_CHECK_LAUNCH(h);
+    k2_scatter_kernel<<<gb, tb, 0, h->stream>>>(meta, B, bins, order, d_out);
+    BP_CHECK_LAUNCH(h);
+    int *h_off = (int *)h->h_pin;
+    BP_CUDA(h, cudaMemcpyAsync(h_off, n_offsets, sizeof(int) * (BP_MAX_N + 2), cudaMemcpyDeviceToHost, h->stream));
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    int off[BP_MAX_N + 2];
+    for (int i = 0; i < BP_MAX_N + 2; ++i) off[i] = h_off[i];
+    for (int n = 0; n <= BP_MAX_N; ++n) {
+        const int count = off[n + 1] - off[n];
+        if (count <= 0) continue;
+        if (n == 0) {
+            k2_empty_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(order, off[n], count, d_out);
+        } else {
+            g_k2_fn[n]<<<count, GW_THREADS, 0, h->stream>>>(dU, m, dS, dT, meta, order, off[n], d_out);
+        }
+        BP_CHECK_LAUNCH(h);
+    }
+    return BP_OK;
+}

@@ -1,0 +1,133 @@
+// guan_walker.cuh -- mixed-radix reflected Gray ("Guan") code walker shared by K2 and K3.
+//
+// The reference iterates Guan codes sequentially from r = 0
+// (theboss/boson_sampling_utilities/permanent_calculators/bs_permanent_calculator_base.py:123-149,
+//  binomial product :151-164).  On the GPU every thread owns a contiguous range of term indices
+// and therefore needs (a) random access: term index -> digit vector, directions and binomial
+// product and (b) the same single-digit +-1 step as the reference.
+//
+// Chin-Huh symmetry: the term of r equals the term of (w - r), so the LAST digit is only walked
+// over [0, floor(w_top/2)] and weighted 2 (1 on the self-paired middle plane when w_top is even).
+// For collision-free input this is exactly Glynn's "one delta fixed" 2^(n-1) space.
+#pragma once
+#include "bp_common.cuh"
+
+#define GW_THREADS 128
+
+struct GuanItem {                 // block-uniform description of one walk, lives in shared memory
+    int D;                        // number of digits (distinct occupied modes on the walk side)
+    int n;                        // particles
+    unsigned long long terms;     // prod (lim + 1)
+    unsigned char lim[BP_MAX_N];  // largest value of digit v
+    unsigned char mult[BP_MAX_N]; // multiplicity w_v of digit v (binomial C(w_v, r_v), coefficient w_v - 2 r_v)
+    short mode[BP_MAX_N];         // mode index of digit v
+};
+
+// Orders the digits of an occupation vector: all occupied modes in mode order, except that the
+// digit chosen as "top" (an odd multiplicity if there is one, else the largest) is moved last.
+// Single-thread helper (called by thread 0 of a block).  Returns the halved term count.
+__device__ inline unsigned long long guan_item_build(GuanItem &it, const unsigned char *occ, int m) {
+    int D = 0, n = 0, top = -1, top_w = 0;
+    for (int v = 0; v < m; ++v) {
+        const int w = occ[v];
+        if (!w) continue;
+        n += w;
+        const bool better = (top < 0) || ((w & 1) && !(top_w & 1)) || (((w & 1) == (top_w & 1)) && w > top_w);
+        if (better) { top = D; top_w = w; }
+        if (D < BP_MAX_N) { it.mode[D] = (short)v; it.mult[D] = (unsigned char)w; }
+        ++D;
+    }
+    it.D = D; it.n = n;
+    if (D == 0 || D > BP_MAX_N) { it.terms = (D == 0) ? 1ull : 0ull; return it.terms; }
+    // move the top digit to the end
+    const short tm = it.mode[top];
+    const unsigned char tw = it.mult[top];
+    for (int v = top; v + 1 < D; ++v) { it.mode[v] = it.mode[v + 1]; it.mult[v] = it.mult[v + 1]; }
+    it.mode[D - 1] = tm; it.mult[D - 1] = tw;
+    unsigned long long terms = 1;
+    for (int v = 0; v < D; ++v) {
+        it.lim[v] = (v == D - 1) ? (unsigned char)(it.mult[v] >> 1) : it.mult[v];
+        terms *= (unsigned long long)(it.lim[v] + 1);
+    }
+    it.terms = terms;
+    return terms;
+}
+
+// Term count of the halved walk without building the item (cost model of the scheduler).
+__device__ inline double guan_terms_of(const unsigned char *occ, int m) {
+    double full = 1.0;
+    int best_w = 0;
+    bool any = false;
+    for (int v = 0; v < m; ++v) {
+        const int w = occ[v];
+        if (!w) continue;
+        full *= (double)(w + 1);
+        const bool better = !any || ((w & 1) && !(best_w & 1)) || (((w & 1) == (best_w & 1)) && w > best_w);
+        if (better) { best_w = w; any = true; }
+    }
+    if (!any) return 1.0;
+    return full / (double)(best_w + 1) * (double)((best_w >> 1) + 1);
+}
+
+struct GuanState {                // per-thread
+    unsigned long long dirmask;   // bit v set: digit v currently moves downwards
+    double binom;                 // prod_v C(w_v, r_v) * (top weight 1 or 2), exact integer
+};
+
+__device__ __forceinline__ double gw_binom(int w, int r) {   // exact for w <= 40
+    if (r > w - r) r = w - r;
+    double c = 1.0;
+    for (int q = 1; q <= r; ++q) c = rint(c * (double)(w - q + 1) / (double)q);
+    return c;
+}
+
+__device__ __forceinline__ double gw_top_weight(const GuanItem &it, int r_top) {
+    return (2 * r_top < (int)it.mult[it.D - 1]) ? 2.0 : 1.0;
+}
+
+// Random access (Appendix A.6): digits r[v * GW_THREADS] (caller passes its own column), directions
+// and binomial product of term index I.
+__device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsigned char *r, GuanState &st) {
+    unsigned long long q = I;
+    st.dirmask = 0ull;
+    double b = 1.0;
+    for (int v = 0; v < it.D; ++v) {
+        const unsigned R = (unsigned)it.lim[v] + 1u;
+        const unsigned d = (unsigned)(q % R);
+        q /= R;
+        int rv;
+        if (q & 1ull) { rv = (int)it.lim[v] - (int)d; st.dirmask |= (1ull << v); }
+        else          { rv = (int)d; }
+        r[v * GW_THREADS] = (unsigned char)rv;
+        if (it.mult[v] > 1) b *= gw_binom(it.mult[v], rv);
+    }
+    st.binom = b * gw_top_weight(it, r[(it.D - 1) * GW_THREADS]);
+}
+
+// One Guan step.  Returns the digit that changed; `delta` = +1 / -1.  Must not be called on the
+// last term of the walk.  __ldg-free: everything is in shared memory / registers.
+__device__ __forceinline__ int guan_step(const GuanItem &it, unsigned char *r, GuanState &st, int &delta) {
+    int v = 0;
+    int cur, nxt, dir;
+    for (;;) {
+        cur = r[v * GW_THREADS];
+        dir = ((st.dirmask >> v) & 1ull) ? -1 : 1;
+        nxt = cur + dir;
+        if (nxt >= 0 && nxt <= (int)it.lim[v]) break;
+        st.dirmask ^= (1ull << v);
+        ++v;
+    }
+    r[v * GW_THREADS] = (unsigned char)nxt;
+    delta = dir;
+    const int w = it.mult[v];
+    if (w > 1) {
+        // C(w, nxt) from C(w, cur): exact integer arithmetic in doubles (values < 2^51)
+        double b = st.binom;
+        if (v == it.D - 1) b /= gw_top_weight(it, cur);   // divide by 1 or 2: exact
+        if (dir > 0) b = rint(b * (double)(w - cur) / (double)nxt);
+        else         b = rint(b * (double)cur / (double)(w - nxt));
+        if (v == it.D - 1) b *= gw_top_weight(it, nxt);
+        st.binom = b;
+    }
+    return v;
+}

@@ -1,0 +1,21 @@
+// minors.cuh -- interface between minors_kernel.cu (K3) and sampler_kernel.cu (K4 + C ABI).
+#pragma once
+#include "bp_common.cuh"
+
+struct K3Finish {
+    const double *U; int m; int W; int chunks; int step;       // step = k - 1 (0-based)
+    const double *partials;
+    unsigned char *occ_s, *occ_t;                              // [samples][m]
+    double *minors_out;                                        // NULL or [samples][m] complex
+    double *pmf_out;                                           // NULL or [samples][m]
+    // sampling state (all NULL for the calculator entry points)
+    const double *tape; int tape_stride;                       // [samples][1 + 2n]
+    unsigned char *remaining; int *n_remaining; int n;         // [samples][n], [samples]
+    const int *steps_total;                                    // [samples]
+};
+
+int bp_k3_width(int k);
+int bp_k3_chunks(bp_context *h, int k, long long samples);
+int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_s, const unsigned char *d_t,
+                 const int *d_steps_total, int k, long long samples, int chunks, double *d_partials);
+int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples);

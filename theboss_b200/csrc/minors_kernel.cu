@@ -1,0 +1,362 @@
+// minors_kernel.cu -- K3: all one-input-particle-removed permanents of a GCC-B step, batched over
+// samples, plus the finish kernel (chunk reduction, Laplace combine into the step's pmf, and the
+// categorical draw / state update of the sampling loop).
+//
+// Replaces BSCC{Ryser,CH}SubmatricesPermanentCalculator.compute_permanents
+// (reference: theboss/boson_sampling_utilities/permanent_calculators/
+//  bs_submatrices_permanent_calculator_base.py:150-189, bs_cc_ryser_submatrices_permanent_calculator.py:73-119,
+//  bs_cc_ch_submatrices_permanent_calculator.py:51-105) and the consumer
+// GeneralizedCliffordsBSimulationStrategy._compute_pmf / _sample_from_pmf / _update_current_input
+// (theboss/simulation_strategies/generalized_cliffords_b_simulation_strategy.py:69-110).
+//
+// Layout (perm A = perm A^T): the Guan walk runs over the k-1 already
+// sampled OUTPUT particles (multiplicities t, r <-> t - r symmetry halved), the product runs over
+// the k INPUT particles (columns of U repeated by s):
+//     c_col(rho) = sum_j (t_j - 2 rho_j) U[j][mode(col)]
+//     P_col      = 2^-(k-1) sum_rho (-1)^{sum rho} prod_j C(t_j, rho_j) prod_{col' != col} c_col'
+// All k leave-one-out products of a term come from prefix x suffix products: ~3k complex
+// multiplies per term instead of k^2.
+//
+// Thread mapping: LPG (1, 2, 4 or 8) adjacent lanes form a group that walks one contiguous range
+// of terms; each lane owns C columns (LPG * C >= k, padding columns are the constant 1).  A lane
+// keeps c[C], prefix[C] and its C accumulators in registers; the product of the OTHER lanes'
+// column products reaches it through an xor-butterfly of warp shuffles and seeds its suffix pass,
+// so splitting costs only (log2 LPG) complex multiplies per term.
+#include "bp_common.cuh"
+#include "guan_walker.cuh"
+#include "minors.cuh"
+
+// shuffle inside one lane group only: groups of a warp may run different trip counts
+__device__ __forceinline__ cplx cshfl_xor(unsigned gmask, cplx a, int mask) {
+    cplx r;
+    r.re = __shfl_xor_sync(gmask, a.re, mask);
+    r.im = __shfl_xor_sync(gmask, a.im, mask);
+    return r;
+}
+
+// dynamic shared memory carve-up (bytes)
+__host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
+    size_t x2 = (size_t)rows * W * sizeof(double2);
+    size_t red = (size_t)GW_THREADS * C * sizeof(double2);
+    size_t dig = (size_t)rows * GW_THREADS;
+    return ((x2 > red ? x2 : red) + dig + 15) / 16 * 16 + 16;
+}
+
+template <int LPG, int C>
+struct K3Cfg {
+    static constexpr int MINB = (C <= 5) ? 4 : 3;
+};
+
+// grid = (chunks, samples).  occ_s / occ_t: [samples][m] uint8 occupations (current input with the
+// newly added particle; outputs sampled so far).  active: NULL or [samples] (0 = skip sample).
+// partials: [samples][chunks][LPG*C][4] double-double partial sums.
+template <int LPG, int C>
+__global__ void __launch_bounds__(GW_THREADS, K3Cfg<LPG, C>::MINB)
+k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ occ_s,
+                 const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, int step,
+                 double *__restrict__ partials) {
+    constexpr int W = LPG * C;
+    constexpr int GROUPS = GW_THREADS / LPG;
+    extern __shared__ __align__(16) unsigned char k3_smem[];
+    __shared__ GuanItem item;
+    __shared__ short col_mode[W];
+
+    const int sample = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    double *my_part = partials + ((size_t)sample * chunks + chunk) * (size_t)(W * 4);
+    if (steps_total && step >= steps_total[sample]) return;   // uniform-loss variant: this sample is complete
+
+    const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
+    if (threadIdx.x == 0) {
+        guan_item_build(item, t, m);
+        int c = 0;
+        for (int v = 0; v < m; ++v)
+            for (int a = 0; a < s[v] && c < W; ++a) col_mode[c++] = (short)v;
+        for (; c < W; ++c) col_mode[c] = -1;
+    }
+    __syncthreads();
+    const int D = item.D;
+    double2 *X2 = reinterpret_cast<double2 *>(k3_smem);
+    size_t x2_bytes = (size_t)D * W * sizeof(double2), red_bytes = (size_t)GW_THREADS * C * sizeof(double2);
+    unsigned char *rdig = k3_smem + ((x2_bytes > red_bytes ? x2_bytes : red_bytes) + 15) / 16 * 16;
+    const double2 *U2 = reinterpret_cast<const double2 *>(U);
+    for (int e = threadIdx.x; e < D * W; e += GW_THREADS) {
+        const int v = e / W, c = e - v * W;
+        const int cm = col_mode[c];
+        double2 x = make_double2(0.0, 0.0);
+        if (cm >= 0) { const double2 u = U2[(int)item.mode[v] * m + cm]; x = make_double2(2.0 * u.x, 2.0 * u.y); }
+        X2[e] = x;
+    }
+    __syncthreads();
+
+    const int lane_in_group = threadIdx.x % LPG, group = threadIdx.x / LPG;
+    const unsigned long long total = item.terms;
+    const unsigned long long ngroups = (unsigned long long)chunks * GROUPS;
+    unsigned long long span = (total + ngroups - 1) / ngroups;
+    if (span < 1) span = 1;
+    const unsigned long long start = ((unsigned long long)chunk * GROUPS + group) * span;
+    const int col0 = lane_in_group * C;
+    const unsigned gmask = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << ((threadIdx.x & 31) / LPG * LPG));
+
+    double ar[C], ai[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) { ar[j] = 0.0; ai[j] = 0.0; }
+
+    // loop bounds are uniform inside a lane group and the shuffles are masked to the group, so
+    // groups of one warp may run different trip counts.
+    if (start < total) {
+        const unsigned long long end = (total - start < span) ? total : start + span;
+        unsigned char *r = rdig + threadIdx.x;
+        GuanState st;
+        guan_seek(item, start, r, st);
+        double cr[C], ci[C];
+#pragma unroll
+        for (int j = 0; j < C; ++j) { cr[j] = 0.0; ci[j] = 0.0; }
+#pragma unroll 1
+        for (int v = 0; v < D; ++v) {
+            const double coef = 0.5 * (double)((int)item.mult[v] - 2 * (int)r[v * GW_THREADS]);
+            const double2 *row = X2 + v * W + col0;
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const double2 a = row[j];
+                cr[j] = fma(coef, a.x, cr[j]);
+                ci[j] = fma(coef, a.y, ci[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
+
+#pragma unroll 1
+        for (unsigned long long I = start; I < end; ++I) {
+            // ---- prefix products over this lane's columns
+            cplx pre[C];
+            pre[0].re = 1.0; pre[0].im = 0.0;
+            if (C > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
+#pragma unroll
+            for (int j = 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
+            cplx tot;
+            if (C > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; tot = cmul(pre[C - 1], cl); }
+            else       { tot.re = cr[0]; tot.im = ci[0]; }
+            // ---- product of the other lanes' totals (xor butterfly inside the group)
+            cplx oth = {1.0, 0.0};
+            if (LPG > 1) {
+                cplx all = tot;
+#pragma unroll
+                for (int mask = 1; mask < LPG; mask <<= 1) {
+                    const cplx x = cshfl_xor(gmask, all, mask);
+                    oth = (mask == 1) ? x : cmul(oth, x);
+                    if ((mask << 1) < LPG) all = cmul(all, x);
+                }
+            }
+            const double w = (I & 1ull) ? -st.binom : st.binom;
+            cplx suf = {w * oth.re, w * oth.im};
+            // ---- suffix pass: leave-one-out products, accumulate
+#pragma unroll
+            for (int j = C - 1; j >= 0; --j) {
+                cplx L = (j == 0) ? suf : cmul(pre[j], suf);
+                ar[j] += L.re;
+                ai[j] += L.im;
+                if (j > 0) { cplx cj = {cr[j], ci[j]}; suf = cmul(suf, cj); }
+            }
+            // ---- next Guan code
+            if (I + 1 < end) {
+                int delta;
+                const int v = guan_step(item, r, st, delta);
+                const double sg = (delta > 0) ? -1.0 : 1.0;
+                const double2 *row = X2 + v * W + col0;
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const double2 a = row[j];
+                    cr[j] = fma(sg, a.x, cr[j]);
+                    ci[j] = fma(sg, a.y, ci[j]);
+                }
+            }
+        }
+    }
+
+    // ---- block reduction: column (lane_in_group, j) over the GROUPS groups, double-double
+    __syncthreads();   // X2 is dead from here on; its storage is reused
+    double2 *red = reinterpret_cast<double2 *>(k3_smem);   // [W][GROUPS]
+#pragma unroll
+    for (int j = 0; j < C; ++j) red[(col0 + j) * GROUPS + group] = make_double2(ar[j], ai[j]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += GW_THREADS) {
+        dd re = {0.0, 0.0}, im = {0.0, 0.0};
+        for (int g = 0; g < GROUPS; ++g) {
+            const double2 x = red[c * GROUPS + g];
+            re = dd_add_d(re, x.x);
+            im = dd_add_d(im, x.y);
+        }
+        my_part[4 * c + 0] = re.hi; my_part[4 * c + 1] = re.lo;
+        my_part[4 * c + 2] = im.hi; my_part[4 * c + 3] = im.lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finish kernel: one block per sample.
+//   1. minors[mode] = 2^-(k-1) * sum over chunks of the partials of the first column of that mode
+//      (k == 1: the occupations themselves, bs_submatrices_permanent_calculator_base.py:157-158)
+//   2. pmf[j] = |sum_i s_i P_i U[j][i]|^2, then / total  (generalized_cliffords_b_simulation_strategy.py:82-92)
+//   3. optional sampling update: numpy.random.choice semantics (cumsum, /= last, searchsorted right)
+//      with the tape's u_choice (:107-110), r_sample[j] += 1, then the NEXT step's input particle:
+//      pop index floor(u_pick * #remaining) of the remaining input particles (:102-105).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
+    __shared__ double2 P[BP_MAX_MODES];
+    __shared__ double wgt[BP_MAX_MODES];
+    __shared__ short first_col[BP_MAX_MODES];
+    const int sample = blockIdx.x, m = a.m, k = a.step + 1;
+    if (a.steps_total && a.step >= a.steps_total[sample]) return;
+    unsigned char *s = a.occ_s + (size_t)sample * m, *t = a.occ_t + (size_t)sample * m;
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int v = 0; v < m; ++v) { first_col[v] = s[v] ? (short)c : (short)-1; c += s[v]; }
+    }
+    __syncthreads();
+    const double scale = ldexp(1.0, -(k - 1));
+    for (int v = threadIdx.x; v < m; v += blockDim.x) {
+        double2 p = make_double2(0.0, 0.0);
+        if (k == 1) {
+            p.x = (double)s[v];
+        } else if (first_col[v] >= 0) {
+            dd re = {0.0, 0.0}, im = {0.0, 0.0};
+            const double *base = a.partials + ((size_t)sample * a.chunks) * (size_t)(a.W * 4) + 4 * (int)first_col[v];
+            for (int ch = 0; ch < a.chunks; ++ch) {   // fixed chunk order
+                const double *q = base + (size_t)ch * (a.W * 4);
+                dd x = {q[0], q[1]}, y = {q[2], q[3]};
+                re = dd_add(re, x);
+                im = dd_add(im, y);
+            }
+            p.x = (re.hi + re.lo) * scale;
+            p.y = (im.hi + im.lo) * scale;
+        }
+        P[v] = p;
+        if (a.minors_out) { a.minors_out[2 * ((size_t)sample * m + v)] = p.x; a.minors_out[2 * ((size_t)sample * m + v) + 1] = p.y; }
+    }
+    __syncthreads();
+    if (!a.pmf_out && !a.tape) return;
+    const double2 *U2 = reinterpret_cast<const double2 *>(a.U);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        for (int i = 0; i < m; ++i) {
+            if (!s[i]) continue;
+            // permanent_added = s_i * P_i; permanent_added *= U[j][i]; permanent += permanent_added
+            const double sr = (double)s[i] * P[i].x, si = (double)s[i] * P[i].y;
+            const double2 u = U2[j * m + i];
+            re += __dsub_rn(__dmul_rn(sr, u.x), __dmul_rn(si, u.y));
+            im += __dadd_rn(__dmul_rn(sr, u.y), __dmul_rn(si, u.x));
+        }
+        const double ab = hypot(re, im);   // abs(permanent) ** 2
+        wgt[j] = ab * ab;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int j = 0; j < m; ++j) total += wgt[j];            // python sum(): sequential
+        for (int j = 0; j < m; ++j) wgt[j] = wgt[j] / total;
+    }
+    __syncthreads();
+    if (a.pmf_out)
+        for (int j = threadIdx.x; j < m; j += blockDim.x) a.pmf_out[(size_t)sample * m + j] = wgt[j];
+    if (!a.tape) return;
+    if (threadIdx.x == 0) {
+        const double *tp = a.tape + (size_t)sample * a.tape_stride;
+        // numpy.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side='right')
+        double run = 0.0;
+        for (int j = 0; j < m; ++j) { run += wgt[j]; wgt[j] = run; }
+        const double last = wgt[m - 1], u = tp[2 + 2 * a.step];
+        int idx = 0;
+        for (int j = 0; j < m; ++j) if (wgt[j] / last <= u) idx = j + 1;
+        if (idx >= m) idx = m - 1;
+        t[idx] += 1;
+        // next step's input particle
+        const int nsteps = a.steps_total ? a.steps_total[sample] : a.n;
+        if (a.step + 1 < nsteps) {
+            int nr = a.n_remaining[sample];
+            unsigned char *rem = a.remaining + (size_t)sample * a.n;
+            int pick = (int)(tp[1 + 2 * (a.step + 1)] * (double)nr);
+            if (pick >= nr) pick = nr - 1;
+            const int mode = rem[pick];
+            for (int q = pick; q + 1 < nr; ++q) rem[q] = rem[q + 1];   // list.pop(pick)
+            a.n_remaining[sample] = nr - 1;
+            s[mode] += 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------
+typedef void (*k3_fn)(const double *, int, const unsigned char *, const unsigned char *, const int *, int, double *);
+
+struct K3Variant { k3_fn fn; int lpg, c; };
+static K3Variant g_k3[4][8];   // [log2 LPG][C]
+static bool g_k3_init = false;
+
+template <int LPG, int C>
+static void k3_reg(int lg) {
+    g_k3[lg][C].fn = k3_minors_kernel<LPG, C>;
+    g_k3[lg][C].lpg = LPG;
+    g_k3[lg][C].c = C;
+}
+template <int LPG>
+static void k3_reg_all(int lg) {
+    k3_reg<LPG, 1>(lg); k3_reg<LPG, 2>(lg); k3_reg<LPG, 3>(lg); k3_reg<LPG, 4>(lg);
+    k3_reg<LPG, 5>(lg); k3_reg<LPG, 6>(lg); k3_reg<LPG, 7>(lg);
+}
+
+// Smallest padded width LPG * C >= k with C <= 7, preferring fewer lanes per group.
+static K3Variant k3_pick(int k) {
+    if (!g_k3_init) { k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3); g_k3_init = true; }
+    int best_lg = -1, best_c = 0, best_w = 1 << 30;
+    for (int lg = 0; lg < 4; ++lg) {
+        const int lpg = 1 << lg;
+        const int c = (k + lpg - 1) / lpg;
+        if (c > 7) continue;
+        if (lpg * c < best_w) { best_w = lpg * c; best_lg = lg; best_c = c; }
+    }
+    K3Variant none = {nullptr, 0, 0};
+    return best_lg < 0 ? none : g_k3[best_lg][best_c];
+}
+
+int bp_k3_width(int k) { K3Variant v = k3_pick(k); return v.fn ? v.lpg * v.c : 0; }
+
+// chunks per sample for step k over `samples` samples
+int bp_k3_chunks(bp_context *h, int k, long long samples) {
+    if (k <= 1) return 1;
+    K3Variant v = k3_pick(k);
+    const double max_terms = ldexp(1.0, k - 2);
+    const int groups = GW_THREADS / (v.lpg ? v.lpg : 1);
+    long long by_work = (long long)(max_terms / (double)(groups * 48));   // >= 48 terms per group
+    if (by_work < 1) by_work = 1;
+    long long by_fill = ((long long)h->sm_count * 16 + samples - 1) / samples;   // ~4 waves of 4 blocks/SM
+    if (by_fill < 1) by_fill = 1;
+    long long ch = by_work < by_fill ? by_work : by_fill;
+    if (ch > 65535) ch = 65535;
+    return (int)ch;
+}
+
+// Enqueue the minors main kernel for step k (= particles in occ_s) over `samples` samples.
+int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_s, const unsigned char *d_t,
+                 const int *d_steps_total, int k, long long samples, int chunks, double *d_partials) {
+    if (k <= 1) return BP_OK;   // handled by the finish kernel
+    K3Variant v = k3_pick(k);
+    if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= 56, got %d", k);
+    if (k - 1 > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k - 1 <= %d, got k = %d", BP_MAX_N, k);
+    if (samples > 65535) return bp_fail(h, BP_ERR_INVALID, "bp_k3_launch: at most 65535 samples per launch");
+    const size_t smem = k3_smem_bytes(k - 1, v.lpg * v.c, v.c);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)chunks, (unsigned)samples);
+    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, m, d_s, d_t, d_steps_total, k - 1, d_partials);
+    BP_CHECK_LAUNCH(h);
+    return BP_OK;
+}
+
+int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples) {
+    k3_finish_kernel<<<(unsigned)samples, 256, 0, h->stream>>>(a);
+    BP_CHECK_LAUNCH(h);
+    return BP_OK;
+}

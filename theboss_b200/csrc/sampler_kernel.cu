@@ -1,0 +1,262 @@
+// sampler_kernel.cu -- K4: device-resident GCC-B sampling loop around the minors kernel (K3), and
+// the C ABI entry points bp_minors / bp_gccb_pmf / bp_gccb_simulate.
+//
+// Replaces GeneralizedCliffordsBSimulationStrategy.simulate / _fill_r_sample
+// (reference: theboss/simulation_strategies/generalized_cliffords_b_simulation_strategy.py:41-67, :94-110)
+// and GeneralizedCliffordsBUniformLossesSimulationStrategy.simulate
+// (theboss/simulation_strategies/generalized_cliffords_b_uniform_losses_simulation_strategy.py:50-121).
+//
+// All samples of a batch advance in lock step: step k launches the minors kernel over
+// (chunks x samples) blocks and one finish kernel that reduces the chunks, forms the pmf, draws the
+// output mode and admits the next input particle.  No host synchronisation inside the loop; every
+// random decision comes from the decision tape (include/bossperm.h).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "bp_common.cuh"
+#include "guan_walker.cuh"
+#include "minors.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator: uniform(seed, sample, slot) does not depend on how the
+// samples are split over launches or GPUs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(unsigned &c0, unsigned &c1, unsigned &c2, unsigned &c3, unsigned k0, unsigned k1) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__device__ inline double philox_uniform(unsigned long long seed, unsigned long long sample, unsigned slot) {
+    unsigned c0 = (unsigned)sample, c1 = (unsigned)(sample >> 32), c2 = slot, c3 = 0x5bd1e995u;
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const unsigned long long bits = (((unsigned long long)c0 << 32) | c1) >> 11;   // 53 bits
+    return (double)bits * (1.0 / 9007199254740992.0);                               // [0, 1)
+}
+
+__global__ void k4_fill_tape_kernel(double *__restrict__ tape, long long samples, int stride, unsigned long long seed,
+                                    long long first_sample) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= samples * stride) return;
+    const long long sample = i / stride;
+    const int slot = (int)(i - sample * stride);
+    tape[i] = philox_uniform(seed, (unsigned long long)(first_sample + sample), (unsigned)slot);
+}
+
+// One thread per sample: particle number (uniform-loss inverse CDF,
+// generalized_cliffords_b_uniform_losses_simulation_strategy.py:67-85), remaining-particle list
+// (mode assignment, boson_sampling_utilities.py:61-78), empty states, and the first input particle.
+__global__ void k4_init_kernel(const unsigned char *__restrict__ s0, int m, int n, const double *__restrict__ loss_weights,
+                               const double *__restrict__ tape, int tape_stride, long long samples,
+                               unsigned char *__restrict__ occ_s, unsigned char *__restrict__ occ_t,
+                               unsigned char *__restrict__ remaining, int *__restrict__ n_remaining,
+                               int *__restrict__ steps_total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= samples) return;
+    const double *tp = tape + i * tape_stride;
+    int steps = n;
+    if (loss_weights) {
+        steps = 0;
+        double run = 0.0;
+        const double u = tp[0];
+        bool found = false;
+        for (int l = 0; l <= n; ++l) {
+            run += loss_weights[l];
+            if (run > u) { found = true; break; }
+            ++steps;
+        }
+        if (!found) steps = n;   // rounding left the CDF below u: the reference would index past the end; clamp
+    }
+    steps_total[i] = steps;
+    unsigned char *s = occ_s + i * m, *t = occ_t + i * m, *rem = remaining + i * (long long)n;
+    for (int v = 0; v < m; ++v) { s[v] = 0; t[v] = 0; }
+    int c = 0;
+    for (int v = 0; v < m; ++v)
+        for (int a = 0; a < s0[v]; ++a) rem[c++] = (unsigned char)v;
+    int nr = n;
+    if (steps > 0) {
+        int pick = (int)(tp[1] * (double)nr);
+        if (pick >= nr) pick = nr - 1;
+        const int mode = rem[pick];
+        for (int q = pick; q + 1 < nr; ++q) rem[q] = rem[q + 1];
+        --nr;
+        s[mode] = 1;
+    }
+    n_remaining[i] = nr;
+}
+
+__global__ void k4_output_kernel(const unsigned char *__restrict__ occ_t, long long count, int *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (int)occ_t[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+static int occ_to_u8(bp_context *h, const int32_t *v, int m, unsigned char *dst, long *sum, const char *who) {
+    long n = 0;
+    for (int i = 0; i < m; ++i) {
+        if (v[i] < 0 || v[i] > 255) return bp_fail(h, BP_ERR_INVALID, "%s: occupation %d out of range", who, v[i]);
+        dst[i] = (unsigned char)v[i];
+        n += v[i];
+    }
+    *sum = n;
+    return BP_OK;
+}
+
+// minors (+ optional pmf) of ONE (s, t) pair; host pointers.
+static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, const int32_t *t, double *minors,
+                       double *pmf, const char *who) {
+    if (!h || !U || !s || !t) return bp_fail(h, BP_ERR_INVALID, "%s: NULL argument", who);
+    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: m=%d outside [1, %d]", who, m, BP_MAX_MODES);
+    BP_CUDA(h, cudaSetDevice(h->device));
+    const size_t ub = sizeof(double) * 2 * (size_t)m * m;
+    int rc;
+    if ((rc = bp_reserve_pinned(h, 2 * (size_t)m + 64 + sizeof(double) * 3 * (size_t)m))) return rc;
+    unsigned char *hs = (unsigned char *)h->h_pin, *ht = hs + m;
+    long k = 0, kt = 0;
+    if ((rc = occ_to_u8(h, s, m, hs, &k, who))) return rc;
+    if ((rc = occ_to_u8(h, t, m, ht, &kt, who))) return rc;
+    if (k < 1) return bp_fail(h, BP_ERR_SHAPE, "%s: the input state holds no particle", who);
+    if (kt != k - 1) return bp_fail(h, BP_ERR_SHAPE, "%s: sum(t) = %ld must equal sum(s) - 1 = %ld", who, kt, k - 1);
+    if (k - 1 > BP_MAX_N || bp_k3_width((int)k) == 0) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: k = %ld too large", who, k);
+    const int chunks = bp_k3_chunks(h, (int)k, 1), W = bp_k3_width((int)k);
+    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_STATE, 2 * (size_t)m + 32))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)(W > 0 ? W : 1) * chunks))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(double) * 3 * (size_t)m))) return rc;
+    BP_CUDA(h, cudaMemcpyAsync(h->d_buf[BP_SLOT_AUX], U, ub, cudaMemcpyHostToDevice, h->stream));
+    unsigned char *d_s = (unsigned char *)h->d_buf[BP_SLOT_STATE], *d_t = d_s + m;
+    BP_CUDA(h, cudaMemcpyAsync(d_s, hs, 2 * (size_t)m, cudaMemcpyHostToDevice, h->stream));
+    const double *dU = (const double *)h->d_buf[BP_SLOT_AUX];
+    double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
+    if ((rc = bp_k3_launch(h, dU, m, d_s, d_t, nullptr, (int)k, 1, chunks, d_part))) return rc;
+    double *d_min = (double *)h->d_buf[BP_SLOT_OUT], *d_pmf = d_min + 2 * (size_t)m;
+    K3Finish a;
+    memset(&a, 0, sizeof(a));
+    a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = (int)k - 1; a.partials = d_part;
+    a.occ_s = d_s; a.occ_t = d_t; a.minors_out = d_min; a.pmf_out = pmf ? d_pmf : nullptr;
+    if ((rc = bp_k3_finish_launch(h, a, 1))) return rc;
+    double *hres = (double *)((char *)h->h_pin + ((2 * (size_t)m + 63) / 64) * 64);
+    BP_CUDA(h, cudaMemcpyAsync(hres, d_min, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (minors) memcpy(minors, hres, sizeof(double) * 2 * (size_t)m);
+    if (pmf) memcpy(pmf, hres + 2 * (size_t)m, sizeof(double) * (size_t)m);
+    return BP_OK;
+}
+
+extern "C" {
+
+int bp_minors(bp_handle h, const double *U, int m, const int32_t *s, const int32_t *t, int formula, double *out) {
+    if (!out) return bp_fail(h, BP_ERR_INVALID, "bp_minors: out is NULL");
+    if (formula < BP_FORMULA_RYSER || formula > BP_FORMULA_GLYNN) return bp_fail(h, BP_ERR_INVALID, "bp_minors: formula %d", formula);
+    return minors_host(h, U, m, s, t, out, nullptr, "bp_minors");
+}
+
+int bp_gccb_pmf(bp_handle h, const double *U, int m, const int32_t *s, const int32_t *t, double *pmf, double *minors_out) {
+    if (!pmf) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_pmf: pmf is NULL");
+    return minors_host(h, U, m, s, t, minors_out, pmf, "bp_gccb_pmf");
+}
+
+int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int64_t n_samples, double eta, uint64_t seed,
+                     int64_t first_sample, const double *tape, int32_t *out) {
+    if (!h || !U || !s || !out) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate: NULL argument");
+    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_gccb_simulate: m=%d outside [1, %d]", m, BP_MAX_MODES);
+    if (n_samples < 0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate: n_samples=%lld", (long long)n_samples);
+    if (eta > 1.0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate: eta=%g > 1", eta);
+    if (n_samples == 0) return BP_OK;
+    BP_CUDA(h, cudaSetDevice(h->device));
+    std::vector<unsigned char> s8((size_t)m);
+    long nl = 0;
+    int rc;
+    if ((rc = occ_to_u8(h, s, m, s8.data(), &nl, "bp_gccb_simulate"))) return rc;
+    const int n = (int)nl;
+    if (n == 0) { memset(out, 0, sizeof(int32_t) * (size_t)n_samples * m); return BP_OK; }
+    if (n - 1 > BP_MAX_N || bp_k3_width(n) == 0) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_gccb_simulate: n=%d too large", n);
+    const int stride = 1 + 2 * n;
+
+    // binomial weights C(n,l) eta^l (1-eta)^(n-l), same expression as the reference (:62-65)
+    std::vector<double> weights;
+    if (eta >= 0.0) {
+        weights.resize(n + 1);
+        for (int l = 0; l <= n; ++l) {
+            double b = 1.0;
+            for (int q = 1; q <= l; ++q) b = b * (double)(n - l + q) / (double)q;   // exact for these sizes
+            b = nearbyint(b);
+            weights[l] = b * pow(eta, (double)l) * pow(1.0 - eta, (double)(n - l));
+        }
+    }
+
+    const long long batch_cap = 32768;
+    const long long batch = n_samples < batch_cap ? n_samples : batch_cap;
+    int max_chunks = 1, maxW = 1;
+    for (int k = 2; k <= n; ++k) {
+        const int ch = bp_k3_chunks(h, k, batch), W = bp_k3_width(k);
+        if ((long long)ch * W > (long long)max_chunks * maxW) { max_chunks = ch; maxW = W; }
+    }
+    const size_t ub = sizeof(double) * 2 * (size_t)m * m;
+    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 8) + (size_t)m + 256;
+    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub + sizeof(double) * (size_t)(n + 2)))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_STATE, state_bytes))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_TAPE, sizeof(double) * (size_t)batch * stride))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)maxW * max_chunks * (size_t)batch))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(int) * (size_t)batch * m))) return rc;
+
+    double *dU = (double *)h->d_buf[BP_SLOT_AUX];
+    double *d_w = dU + 2 * (size_t)m * m;
+    BP_CUDA(h, cudaMemcpyAsync(dU, U, ub, cudaMemcpyHostToDevice, h->stream));
+    if (eta >= 0.0) BP_CUDA(h, cudaMemcpyAsync(d_w, weights.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+    // state carve-up: ints first (alignment), then bytes
+    char *base = (char *)h->d_buf[BP_SLOT_STATE];
+    int *d_nrem = (int *)base;
+    int *d_steps = d_nrem + batch;
+    unsigned char *d_occ_s = (unsigned char *)(d_steps + batch);
+    unsigned char *d_occ_t = d_occ_s + (size_t)batch * m;
+    unsigned char *d_rem = d_occ_t + (size_t)batch * m;
+    unsigned char *d_s0 = d_rem + (size_t)batch * n;
+    BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data(), (size_t)m, cudaMemcpyHostToDevice, h->stream));
+    double *d_tape = (double *)h->d_buf[BP_SLOT_TAPE];
+    double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
+    int *d_out = (int *)h->d_buf[BP_SLOT_OUT];
+
+    for (long long done = 0; done < n_samples; done += batch) {
+        const long long S = (n_samples - done < batch) ? (n_samples - done) : batch;
+        if (tape) {
+            BP_CUDA(h, cudaMemcpyAsync(d_tape, tape + (size_t)done * stride, sizeof(double) * (size_t)S * stride,
+                                       cudaMemcpyHostToDevice, h->stream));
+        } else {
+            const long long tot = S * stride;
+            k4_fill_tape_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(d_tape, S, stride, seed, first_sample + done);
+            BP_CHECK_LAUNCH(h);
+        }
+        k4_init_kernel<<<(unsigned)((S + 127) / 128), 128, 0, h->stream>>>(d_s0, m, n, eta >= 0.0 ? d_w : nullptr, d_tape, stride, S,
+                                                                          d_occ_s, d_occ_t, d_rem, d_nrem, d_steps);
+        BP_CHECK_LAUNCH(h);
+        for (int k = 1; k <= n; ++k) {
+            const int chunks = bp_k3_chunks(h, k, S), W = bp_k3_width(k);
+            if ((rc = bp_k3_launch(h, dU, m, d_occ_s, d_occ_t, d_steps, k, S, chunks, d_part))) return rc;
+            K3Finish a;
+            memset(&a, 0, sizeof(a));
+            a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = k - 1; a.partials = d_part;
+            a.occ_s = d_occ_s; a.occ_t = d_occ_t;
+            a.tape = d_tape; a.tape_stride = stride; a.remaining = d_rem; a.n_remaining = d_nrem; a.n = n;
+            a.steps_total = d_steps;
+            if ((rc = bp_k3_finish_launch(h, a, S))) return rc;
+        }
+        const long long cnt = S * m;
+        k4_output_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(d_occ_t, cnt, d_out);
+        BP_CHECK_LAUNCH(h);
+        BP_CUDA(h, cudaMemcpyAsync(out + (size_t)done * m, d_out, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+        BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return BP_OK;
+}
+
+}  // extern "C"
