@@ -165,7 +165,7 @@ int bp_fp64_peak(bp_handle h, double target_ms, double *tflops) {
     if (rc) return rc;
     double *sink = (double *)h->d_buf[BP_SLOT_MISC];
     // calibrate, then run ~target_ms
-    int iters = 1 << 12;
+    int iters = 1 << 10;
     float ms = 0.f;
     double best = 0.0;
     for (int round = 0; round < 4; ++round) {
@@ -177,15 +177,15 @@ int bp_fp64_peak(bp_handle h, double target_ms, double *tflops) {
         BP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         BP_CUDA(h, cudaEventSynchronize(h->ev1));
         BP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        // per launch: sm_count * 8 blocks * 256 threads * 16 chains * iters DFMA
-        double flops = 2.0 * (double)h->sm_count * 8.0 * 256.0 * 16.0 * (double)iters;
+        // per launch: sm_count * 8 blocks * 256 threads * 64 DFMA per iteration
+        double flops = 2.0 * (double)h->sm_count * 8.0 * 256.0 * 64.0 * (double)iters;
         double tf = flops / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
         if (ms >= 0.5 * target_ms) break;
         double scale = target_ms / (ms > 1e-3 ? ms : 1e-3);
         if (scale > 64.0) scale = 64.0;
         iters = (int)(iters * scale);
-        if (iters > (1 << 24)) iters = 1 << 24;
+        if (iters > (1 << 22)) iters = 1 << 22;
     }
     *tflops = best;
     return BP_OK;

@@ -36,7 +36,9 @@ int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int
 }
 
 // ---------------------------------------------------------------------------------------------
-// FP64 peak probe: 16 independent DFMA chains per thread, 256 threads, 8 blocks per SM.
+// FP64 peak probe: 16 independent DFMA chains per thread, 64 DFMAs per loop iteration, 256 threads,
+// 8 blocks per SM.  On B200 this reaches 37.1 TFLOP/s = 148 SM x 64 DFMA/clk x 1.965 GHz (a loop body of
+// only 16 DFMAs loses 11 % to the three loop-control instructions, see profiles/r01_k1_explore.txt).
 // The measured rate (2 flops per DFMA) is the roofline denominator bench.py reports against.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) fp64_peak_kernel(int iters, double *__restrict__ sink) {
@@ -47,7 +49,9 @@ __global__ void __launch_bounds__(256, 2) fp64_peak_kernel(int iters, double *__
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
     }
     double r = 0.0;
 #pragma unroll
