@@ -168,6 +168,74 @@ def cpu_port_sample(target_seconds=12.0):
             "seconds": t}
 
 
+def secondary_metrics(device):
+    """Other BASELINE.json configs of the same hot path, informational (`extra` key).  Each number is
+    wall-clock through the public host-pointer API (copies included), best of a few repeats."""
+    import numpy as np
+
+    from theboss_b200 import _native
+
+    h = _native.default_handle(device)
+    out = {}
+
+    def best_of(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    try:   # C2: 10^4 batched n=20 permanents with repeated rows and columns
+        U, S, T = workloads.c2_batch(items=10_000)
+        t = best_of(lambda: h.perm_batched(U, S, T))
+        terms = 0.0
+        for b in range(S.shape[0]):
+            cs = np.prod(S[b].astype(np.float64) + 1) ; ct = np.prod(T[b].astype(np.float64) + 1)
+            terms += min(cs, ct) / 2
+        out["c2_batched_n20_m40"] = {"items": 10_000, "seconds": t, "permanents_per_s": 10_000 / t,
+                                     "approx_useful_tflops": terms * (6 * 20 + 6 * 19 + 4) / t / 1e12}
+    except Exception as e:   # noqa: BLE001
+        out["c2_batched_n20_m40"] = {"error": repr(e)}
+    try:   # C3: one GCC-B step at n=24, m=48 (all 24 minors + 48 probabilities)
+        for name, cf in (("c3_step_n24_m48_bunched_outputs", False), ("c3_step_n24_m48_collision_free", True)):
+            U, s, tt = workloads.c3_step(24, 48, cf)
+            t = best_of(lambda: h.gccb_pmf(U, s, tt))
+            T_terms = np.prod(tt.astype(np.float64) + 1) / 2
+            out[name] = {"seconds": t, "steps_per_s": 1 / t, "useful_tflops": T_terms * (22 * 24 - 36) / t / 1e12}
+    except Exception as e:   # noqa: BLE001
+        out["c3_step_n24_m48"] = {"error": repr(e)}
+    try:   # GCC-B sampling run at n=24, m=48
+        U = workloads.haar(48, 24)
+        s = np.array([1] * 24 + [0] * 24, dtype=np.int32)
+        S_n = 512
+        t = best_of(lambda: h.gccb_simulate(U, s, S_n, seed=5), reps=2)
+        out["gccb_n24_m48"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t}
+    except Exception as e:   # noqa: BLE001
+        out["gccb_n24_m48"] = {"error": repr(e)}
+    try:   # C5 (i): uniform losses eta = 0.5, n=30, m=60
+        U, U_lossy, s = workloads.c5_lossy(30, 60)
+        S_n = 2000
+        t = best_of(lambda: h.gccb_simulate(U, s, S_n, eta=0.5, seed=5), reps=2)
+        out["c5_uniform_losses_n30_m60"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t}
+    except Exception as e:   # noqa: BLE001
+        out["c5_uniform_losses_n30_m60"] = {"error": repr(e)}
+    try:   # C1: GCC (version A), n=5, m=10, 1000 samples through the strategy class
+        from theboss_b200.boson_sampling_utilities.permanent_calculators.glynn_gray_permanent_calculator import GlynnGrayPermanentCalculator
+        from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy
+        U = workloads.haar(10, 2024)
+        strat = GeneralizedCliffordsSimulationStrategy(GlynnGrayPermanentCalculator(U, None, None, device=device))
+        np.random.seed(7)
+        t0 = time.perf_counter()
+        strat.simulate([1] * 5 + [0] * 5, 1000)
+        t = time.perf_counter() - t0
+        out["c1_gcc_n5_m10"] = {"samples": 1000, "seconds": t, "samples_per_s": 1000 / t, "pmf_layers": len(strat.pmfs)}
+    except Exception as e:   # noqa: BLE001
+        out["c1_gcc_n5_m10"] = {"error": repr(e)}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure
     Python (~2.3 h per n=30 permanent) and /root/reference does not exist on the
@@ -292,6 +360,7 @@ def run_native(args):
         if rel > 1e-10:
             raise SystemExit(f"bench.py: result {result} deviates from the long-double fixture by {rel:.3e}")
         cpu = cpu_port_sample() if world == 1 else None
+        extra = secondary_metrics(local_rank) if (world == 1 and not args.no_extra) else None
         value = args.steps / (total_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -305,8 +374,8 @@ def run_native(args):
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "traffic": None,
-                "kernel": "glynn_gray_kernel<30>", "kernel_ms": k1_ms,
-                "peak_source": "bp_fp64_peak DFMA probe on this GPU in this run (nominal B200 FP64: 37 TFLOP/s)",
+                "kernel": "glynn_block4_kernel<30>", "kernel_ms": k1_ms,
+                "peak_source": "bp_fp64_peak DFMA probe (64 independent DFMA per loop iteration) on this GPU in this run; nominal B200 FP64 = 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
                 "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                 "fp64_issue_slot_frac": (ISSUE_SLOTS * (job.hi - job.lo) / 2.0 ** (N_PHOTONS - 1)) * 2 / (k1_ms * 1e-3) / 1e12 / fp64_peak,
                 "structural_ceiling": (8 * N_PHOTONS - 4) / (12 * N_PHOTONS - 4),
@@ -316,6 +385,8 @@ def run_native(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -328,6 +399,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (informational) configs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

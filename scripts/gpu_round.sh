@@ -10,5 +10,5 @@ tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:glynn_gray_kernel -s 1 -c 1 -f -o gpurun_out/k1_n30 python scripts/profile_k1.py 30 > gpurun_out/ncu_k1.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:glynn_block4_kernel -s 1 -c 1 -f -o gpurun_out/k1_n30 python scripts/profile_k1.py 30 > gpurun_out/ncu_k1.log 2>&1
 tail -3 gpurun_out/ncu_k1.log

@@ -164,13 +164,14 @@ int bp_fp64_peak(bp_handle h, double target_ms, double *tflops) {
     int rc = bp_reserve(h, BP_SLOT_MISC, sizeof(double) * 1024);
     if (rc) return rc;
     double *sink = (double *)h->d_buf[BP_SLOT_MISC];
-    // calibrate, then run ~target_ms
-    int iters = 1 << 10;
+    // fixed-size launches (~target_ms each on a B200), one warm-up, best of three
+    int iters = (int)(50000.0 * target_ms / 52.0);
+    if (iters < 1000) iters = 1000;
     float ms = 0.f;
     double best = 0.0;
-    for (int round = 0; round < 4; ++round) {
-        rc = bp_fp64_peak_launch(h, iters, sink);   // warm-up
-        if (rc) return rc;
+    rc = bp_fp64_peak_launch(h, iters / 4, sink);
+    if (rc) return rc;
+    for (int round = 0; round < 3; ++round) {
         BP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
         rc = bp_fp64_peak_launch(h, iters, sink);
         if (rc) return rc;
@@ -178,14 +179,9 @@ int bp_fp64_peak(bp_handle h, double target_ms, double *tflops) {
         BP_CUDA(h, cudaEventSynchronize(h->ev1));
         BP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         // per launch: sm_count * 8 blocks * 256 threads * 64 DFMA per iteration
-        double flops = 2.0 * (double)h->sm_count * 8.0 * 256.0 * 64.0 * (double)iters;
-        double tf = flops / (ms * 1e-3) / 1e12;
+        const double flops = 2.0 * (double)h->sm_count * 8.0 * 256.0 * 64.0 * (double)iters;
+        const double tf = flops / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
-        if (ms >= 0.5 * target_ms) break;
-        double scale = target_ms / (ms > 1e-3 ? ms : 1e-3);
-        if (scale > 64.0) scale = 64.0;
-        iters = (int)(iters * scale);
-        if (iters > (1 << 22)) iters = 1 << 22;
     }
     *tflops = best;
     return BP_OK;

@@ -100,7 +100,7 @@ template <int N>
 __global__ void __launch_bounds__(GW_THREADS, K2Cfg<N>::MINB)
 k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ S,
                const unsigned char *__restrict__ T, const K2Meta *__restrict__ meta,
-               const int *__restrict__ order, int first, double *__restrict__ out) {
+               const int *__restrict__ order, int first, double *__restrict__ partials) {
     __shared__ GuanItem item;
     __shared__ short col_mode[N];
     __shared__ double2 X2[N * N];                       // 2 * X[v][j], D <= N rows
@@ -108,7 +108,7 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     __shared__ double red[4 * (GW_THREADS / 32)];
 
     const int b = order[first + blockIdx.x];
-    const K2Meta me = meta[b];
+    const K2Meta me = meta[b];   // (blockIdx.y = chunk of this item's walk)
     const unsigned char *walk = (me.walk_outputs ? T : S) + (long long)b * m;
     const unsigned char *prod = (me.walk_outputs ? S : T) + (long long)b * m;
     if (threadIdx.x == 0) {
@@ -129,10 +129,12 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     }
     __syncthreads();
 
+    // grid = (items, chunks): the walk of one item is cut into gridDim.y * GW_THREADS contiguous spans
     const unsigned long long total = item.terms;
-    unsigned long long span = (total + GW_THREADS - 1) / GW_THREADS;
+    const unsigned long long nspans = (unsigned long long)gridDim.y * GW_THREADS;
+    unsigned long long span = (total + nspans - 1) / nspans;
     if (span < 1) span = 1;
-    const unsigned long long start = (unsigned long long)threadIdx.x * span;
+    const unsigned long long start = ((unsigned long long)blockIdx.y * GW_THREADS + threadIdx.x) * span;
     dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
 
     if (start < total) {
@@ -186,10 +188,27 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     }
     block_reduce_dd(acc_re, acc_im, red);
     if (threadIdx.x == 0) {
-        const double scale = ldexp(1.0, -N);                  // 2^-n (chin_huh_permanent_calculator.py:41)
-        out[2 * (long long)b] = (acc_re.hi + acc_re.lo) * scale;
-        out[2 * (long long)b + 1] = (acc_im.hi + acc_im.lo) * scale;
+        double *o = partials + 4 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
+        o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo;
     }
+}
+
+// out[item] = 2^-n * (sum of the item's chunk partials, in chunk order)
+__global__ void k2_finish_kernel(const int *__restrict__ order, int first, int count, int chunks, int n,
+                                 const double *__restrict__ partials, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    dd re = {0.0, 0.0}, im = {0.0, 0.0};
+    const double *p = partials + 4 * (size_t)i * chunks;
+    for (int c = 0; c < chunks; ++c) {
+        dd a = {p[4 * c + 0], p[4 * c + 1]}, b = {p[4 * c + 2], p[4 * c + 3]};
+        re = dd_add(re, a);
+        im = dd_add(im, b);
+    }
+    const double scale = ldexp(1.0, -n);                      // 2^-n (chin_huh_permanent_calculator.py:41)
+    const long long b = order[first + i];
+    out[2 * b] = (re.hi + re.lo) * scale;
+    out[2 * b + 1] = (im.hi + im.lo) * scale;
 }
 
 // items without particles: permanent of the empty matrix = 1
@@ -244,9 +263,21 @@ int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS
         if (count <= 0) continue;
         if (n == 0) {
             k2_empty_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(order, off[n], count, d_out);
-        } else {
-            g_k2_fn[n]<<<count, GW_THREADS, 0, h->stream>>>(dU, m, dS, dT, meta, order, off[n], d_out);
+            BP_CHECK_LAUNCH(h);
+            continue;
         }
+        // chunks per item: enough blocks to fill the GPU a few times over, but at least ~256 terms per thread
+        long long by_fill = ((long long)h->sm_count * 12 + count - 1) / count;
+        long long by_work = (long long)(ldexp(1.0, n - 1) / (GW_THREADS * 256.0));
+        long long chunks = by_fill < by_work ? by_fill : by_work;
+        if (chunks < 1) chunks = 1;
+        if (chunks > 4096) chunks = 4096;
+        if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)count * (size_t)chunks))) return rc;
+        double *d_partials = (double *)h->d_buf[BP_SLOT_PARTIALS];
+        dim3 grid((unsigned)count, (unsigned)chunks);
+        g_k2_fn[n]<<<grid, GW_THREADS, 0, h->stream>>>(dU, m, dS, dT, meta, order, off[n], d_partials);
+        BP_CHECK_LAUNCH(h);
+        k2_finish_kernel<<<(count + 127) / 128, 128, 0, h->stream>>>(order, off[n], count, (int)chunks, n, d_partials, d_out);
         BP_CHECK_LAUNCH(h);
     }
     return BP_OK;

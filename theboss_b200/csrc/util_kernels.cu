@@ -41,7 +41,7 @@ int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int
 // only 16 DFMAs loses 11 % to the three loop-control instructions, see profiles/r01_k1_explore.txt).
 // The measured rate (2 flops per DFMA) is the roofline denominator bench.py reports against.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) fp64_peak_kernel(int iters, double *__restrict__ sink) {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *__restrict__ sink) {
     double a[16];
     const double x = 1.0 + 1e-9 * (double)threadIdx.x, y = 1e-12 * (double)(blockIdx.x + 1);
 #pragma unroll

@@ -50,6 +50,39 @@ def combine_partials(partials: np.ndarray, N: int) -> complex:
     return complex((acc[0][0] + acc[0][1]) * scale, (acc[1][0] + acc[1][1]) * scale)
 
 
+def allgather_partials(partial, group=None):
+    """All-gather one 4-double partial per rank (NCCL on GPU tensors, gloo on CPU tensors) and return
+    the (world_size, 4) tensor in rank order.  Single-process runs return the partial itself."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return partial.reshape(1, 4).clone()
+    world = dist.get_world_size(group)
+    out = torch.empty(4 * world, dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out, partial.contiguous(), group=group)
+    return out.reshape(world, 4)
+
+
+def gather_samples(local_samples, group=None):
+    """Final gather of a sharded sampling run: (S_local, m) integer tensors -> (S_total, m) in rank order.
+    The only collective of a sampling job; shards may differ in size by one."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_samples
+    world = dist.get_world_size(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=local_samples.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([local_samples.shape[0]], dtype=torch.int64, device=local_samples.device), group=group)
+    cap = int(max(int(x.item()) for x in sizes))
+    padded = torch.zeros((cap, local_samples.shape[1]), dtype=local_samples.dtype, device=local_samples.device)
+    padded[: local_samples.shape[0]] = local_samples
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[: int(n.item())] for p, n in zip(parts, sizes)], dim=0)
+
+
 class ShardedGlynnPermanent:
     """perm(A) of one explicit N x N matrix over all ranks of a process group.
 
