@@ -26,7 +26,7 @@ struct GuanItem {                 // block-uniform description of one walk, live
 // Orders the digits of an occupation vector: all occupied modes in mode order, except that the
 // digit chosen as "top" (an odd multiplicity if there is one, else the largest) is moved last.
 // Single-thread helper (called by thread 0 of a block).  Returns the halved term count.
-__device__ inline unsigned long long guan_item_build(GuanItem &it, const unsigned char *occ, int m) {
+__device__ inline unsigned long long guan_item_build(GuanItem &it, const unsigned char *occ, int m, bool inner_first = false) {
     int D = 0, n = 0, top = -1, top_w = 0;
     for (int v = 0; v < m; ++v) {
         const int w = occ[v];
@@ -44,6 +44,14 @@ __device__ inline unsigned long long guan_item_build(GuanItem &it, const unsigne
     const unsigned char tw = it.mult[top];
     for (int v = top; v + 1 < D; ++v) { it.mode[v] = it.mode[v + 1]; it.mult[v] = it.mult[v + 1]; }
     it.mode[D - 1] = tm; it.mult[D - 1] = tw;
+    if (inner_first && D > 2) {
+        // digit 0 becomes the inner loop of the minors kernel: give it the largest multiplicity
+        int best = 0;
+        for (int v = 1; v < D - 1; ++v) if (it.mult[v] > it.mult[best]) best = v;
+        const short bm = it.mode[best]; const unsigned char bw = it.mult[best];
+        it.mode[best] = it.mode[0]; it.mult[best] = it.mult[0];
+        it.mode[0] = bm; it.mult[0] = bw;
+    }
     unsigned long long terms = 1;
     for (int v = 0; v < D; ++v) {
         it.lim[v] = (v == D - 1) ? (unsigned char)(it.mult[v] >> 1) : it.mult[v];
@@ -87,11 +95,12 @@ __device__ __forceinline__ double gw_top_weight(const GuanItem &it, int r_top) {
 
 // Random access (Appendix A.6): digits r[v * GW_THREADS] (caller passes its own column), directions
 // and binomial product of term index I.
-__device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsigned char *r, GuanState &st) {
+// With v0 > 0 the walk runs over digits v0 .. D-1 only (I indexes that sub-walk).
+__device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsigned char *r, GuanState &st, int v0 = 0) {
     unsigned long long q = I;
     st.dirmask = 0ull;
     double b = 1.0;
-    for (int v = 0; v < it.D; ++v) {
+    for (int v = v0; v < it.D; ++v) {
         const unsigned R = (unsigned)it.lim[v] + 1u;
         const unsigned d = (unsigned)(q % R);
         q /= R;
@@ -101,13 +110,13 @@ __device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsig
         r[v * GW_THREADS] = (unsigned char)rv;
         if (it.mult[v] > 1) b *= gw_binom(it.mult[v], rv);
     }
-    st.binom = b * gw_top_weight(it, r[(it.D - 1) * GW_THREADS]);
+    st.binom = (it.D - 1 >= v0) ? b * gw_top_weight(it, r[(it.D - 1) * GW_THREADS]) : b;
 }
 
 // One Guan step.  Returns the digit that changed; `delta` = +1 / -1.  Must not be called on the
 // last term of the walk.  __ldg-free: everything is in shared memory / registers.
-__device__ __forceinline__ int guan_step(const GuanItem &it, unsigned char *r, GuanState &st, int &delta) {
-    int v = 0;
+__device__ __forceinline__ int guan_step(const GuanItem &it, unsigned char *r, GuanState &st, int &delta, int v0 = 0) {
+    int v = v0;
     int cur, nxt, dir;
     for (;;) {
         cur = r[v * GW_THREADS];

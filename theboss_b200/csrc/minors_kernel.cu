@@ -42,6 +42,19 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
     return ((x2 > red ? x2 : red) + dig + 15) / 16 * 16 + 16;
 }
 
+// Number of chunk blocks that actually work on a sample whose walk has `terms` terms: about
+// K3_TERMS_PER_GROUP terms per lane group, at most the launched `chunks`.  Bunched outputs shrink the
+// walk by orders of magnitude, so the grid is sized for the collision-free worst case and blocks beyond
+// `active` exit at once; the finish kernel applies the same rule.
+#define K3_TERMS_PER_GROUP 192ull
+__host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, int groups) {
+    const unsigned long long per_block = K3_TERMS_PER_GROUP * (unsigned long long)groups;
+    unsigned long long a = (terms + per_block - 1) / per_block;
+    if (a < 1) a = 1;
+    if (a > (unsigned long long)chunks) a = (unsigned long long)chunks;
+    return (int)a;
+}
+
 template <int LPG, int C>
 struct K3Cfg {
     static constexpr int MINB = (C <= 5) ? 4 : 3;
@@ -54,7 +67,7 @@ template <int LPG, int C>
 __global__ void __launch_bounds__(GW_THREADS, K3Cfg<LPG, C>::MINB)
 k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ occ_s,
                  const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, int step,
-                 double *__restrict__ partials) {
+                 double *__restrict__ partials, unsigned long long *__restrict__ terms_out) {
     constexpr int W = LPG * C;
     constexpr int GROUPS = GW_THREADS / LPG;
     extern __shared__ __align__(16) unsigned char k3_smem[];
@@ -66,15 +79,23 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
     if (steps_total && step >= steps_total[sample]) return;   // uniform-loss variant: this sample is complete
 
     const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
+    __shared__ double bin0[BP_MAX_N + 2];      // weight table of the inner digit: C(w_0, r) (x top weight if it is the only digit)
+    __shared__ unsigned long long align_rows;  // group ranges are multiples of this many rows
     if (threadIdx.x == 0) {
-        guan_item_build(item, t, m);
+        guan_item_build(item, t, m, /*inner_first=*/true);
         int c = 0;
         for (int v = 0; v < m; ++v)
             for (int a = 0; a < s[v] && c < W; ++a) col_mode[c++] = (short)v;
         for (; c < W; ++c) col_mode[c] = -1;
+        if (item.D > 0)
+            for (int r = 0; r <= (int)item.lim[0]; ++r)
+                bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
     }
     __syncthreads();
     const int D = item.D;
+    const int active = k3_active_chunks(item.terms, chunks, GROUPS);
+    if (chunk == 0 && threadIdx.x == 0) terms_out[sample] = item.terms;
+    if (chunk >= active) return;
     double2 *X2 = reinterpret_cast<double2 *>(k3_smem);
     size_t x2_bytes = (size_t)D * W * sizeof(double2), red_bytes = (size_t)GW_THREADS * C * sizeof(double2);
     unsigned char *rdig = k3_smem + ((x2_bytes > red_bytes ? x2_bytes : red_bytes) + 15) / 16 * 16;
@@ -86,14 +107,30 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
         if (cm >= 0) { const double2 u = U2[(int)item.mode[v] * m + cm]; x = make_double2(2.0 * u.x, 2.0 * u.y); }
         X2[e] = x;
     }
+    // The walk is organised in ROWS: one row = the L0 + 1 terms that differ only in digit 0 (swept up
+    // on even rows, down on odd rows: reflected code); rows are indexed by the sub-walk over digits
+    // 1 .. D-1.  A lane group owns a contiguous range of rows.
+    const int L0 = item.lim[0];
+    const unsigned long long rows = item.terms / (unsigned long long)(L0 + 1);
+    const unsigned long long ngroups = (unsigned long long)active * GROUPS;
+    if (threadIdx.x == 0) {
+        // align the per-group row count to the period of the low digits so that all groups of a warp
+        // take the same branches inside guan_step (the carry pattern of the low digits is then identical)
+        unsigned long long raw = (rows + ngroups - 1) / ngroups, al = 1;
+        for (int v = 1; v < D; ++v) {
+            const unsigned long long nxt = al * (unsigned long long)(item.lim[v] + 1);
+            if (nxt * 4 > raw) break;
+            al = nxt;
+        }
+        align_rows = al;
+    }
     __syncthreads();
 
     const int lane_in_group = threadIdx.x % LPG, group = threadIdx.x / LPG;
-    const unsigned long long total = item.terms;
-    const unsigned long long ngroups = (unsigned long long)chunks * GROUPS;
-    unsigned long long span = (total + ngroups - 1) / ngroups;
-    if (span < 1) span = 1;
-    const unsigned long long start = ((unsigned long long)chunk * GROUPS + group) * span;
+    unsigned long long rspan = (rows + ngroups - 1) / ngroups;
+    rspan = (rspan + align_rows - 1) / align_rows * align_rows;
+    if (rspan < 1) rspan = 1;
+    const unsigned long long row_start = ((unsigned long long)chunk * GROUPS + group) * rspan;
     const int col0 = lane_in_group * C;
     const unsigned gmask = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << ((threadIdx.x & 31) / LPG * LPG));
 
@@ -103,17 +140,22 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
 
     // loop bounds are uniform inside a lane group and the shuffles are masked to the group, so
     // groups of one warp may run different trip counts.
-    if (start < total) {
-        const unsigned long long end = (total - start < span) ? total : start + span;
+    if (row_start < rows) {
+        const unsigned long long row_end = (rows - row_start < rspan) ? rows : row_start + rspan;
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
-        guan_seek(item, start, r, st);
-        double cr[C], ci[C];
+        guan_seek(item, row_start, r, st, /*v0=*/1);
+        int r0 = (row_start & 1ull) ? L0 : 0;          // reflected: odd rows sweep digit 0 downwards
+        int dir0 = (row_start & 1ull) ? -1 : 1;
+        double cr[C], ci[C], x0r[C], x0i[C];
 #pragma unroll
         for (int j = 0; j < C; ++j) { cr[j] = 0.0; ci[j] = 0.0; }
+        int par = r0;                                   // parity of sum(rho) -> sign of the term
 #pragma unroll 1
         for (int v = 0; v < D; ++v) {
-            const double coef = 0.5 * (double)((int)item.mult[v] - 2 * (int)r[v * GW_THREADS]);
+            const int rv = (v == 0) ? r0 : (int)r[v * GW_THREADS];
+            if (v > 0) par += rv;
+            const double coef = 0.5 * (double)((int)item.mult[v] - 2 * rv);
             const double2 *row = X2 + v * W + col0;
 #pragma unroll
             for (int j = 0; j < C; ++j) {
@@ -123,53 +165,69 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
             }
         }
 #pragma unroll
-        for (int j = 0; j < C; ++j)
+        for (int j = 0; j < C; ++j) {
+            const double2 a = X2[col0 + j];             // row of digit 0, kept in registers
+            x0r[j] = a.x; x0i[j] = a.y;
             if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
+        }
+        double sgn = (par & 1) ? -1.0 : 1.0;
 
 #pragma unroll 1
-        for (unsigned long long I = start; I < end; ++I) {
-            // ---- prefix products over this lane's columns
-            cplx pre[C];
-            pre[0].re = 1.0; pre[0].im = 0.0;
-            if (C > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
+        for (unsigned long long q = row_start;;) {
+            // ---- inner sweep over digit 0: L0 + 1 terms, no stepping logic, no row loads
+#pragma unroll 1
+            for (int step = 0;; ++step) {
+                // prefix products over this lane's columns
+                cplx pre[C];
+                pre[0].re = 1.0; pre[0].im = 0.0;
+                if (C > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
 #pragma unroll
-            for (int j = 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
-            cplx tot;
-            if (C > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; tot = cmul(pre[C - 1], cl); }
-            else       { tot.re = cr[0]; tot.im = ci[0]; }
-            // ---- product of the other lanes' totals (xor butterfly inside the group)
-            cplx oth = {1.0, 0.0};
-            if (LPG > 1) {
-                cplx all = tot;
+                for (int j = 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
+                cplx tot;
+                if (C > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; tot = cmul(pre[C - 1], cl); }
+                else       { tot.re = cr[0]; tot.im = ci[0]; }
+                // product of the other lanes' totals (xor butterfly inside the group)
+                cplx oth = {1.0, 0.0};
+                if (LPG > 1) {
+                    cplx all = tot;
 #pragma unroll
-                for (int mask = 1; mask < LPG; mask <<= 1) {
-                    const cplx x = cshfl_xor(gmask, all, mask);
-                    oth = (mask == 1) ? x : cmul(oth, x);
-                    if ((mask << 1) < LPG) all = cmul(all, x);
+                    for (int mask = 1; mask < LPG; mask <<= 1) {
+                        const cplx x = cshfl_xor(gmask, all, mask);
+                        oth = (mask == 1) ? x : cmul(oth, x);
+                        if ((mask << 1) < LPG) all = cmul(all, x);
+                    }
                 }
-            }
-            const double w = (I & 1ull) ? -st.binom : st.binom;
-            cplx suf = {w * oth.re, w * oth.im};
-            // ---- suffix pass: leave-one-out products, accumulate
+                const double w = sgn * st.binom * bin0[r0];
+                cplx suf = {w * oth.re, w * oth.im};
+                // suffix pass: leave-one-out products, accumulate
 #pragma unroll
-            for (int j = C - 1; j >= 0; --j) {
-                cplx L = (j == 0) ? suf : cmul(pre[j], suf);
-                ar[j] += L.re;
-                ai[j] += L.im;
-                if (j > 0) { cplx cj = {cr[j], ci[j]}; suf = cmul(suf, cj); }
-            }
-            // ---- next Guan code
-            if (I + 1 < end) {
-                int delta;
-                const int v = guan_step(item, r, st, delta);
-                const double sg = (delta > 0) ? -1.0 : 1.0;
-                const double2 *row = X2 + v * W + col0;
-#pragma unroll
-                for (int j = 0; j < C; ++j) {
-                    const double2 a = row[j];
-                    cr[j] = fma(sg, a.x, cr[j]);
-                    ci[j] = fma(sg, a.y, ci[j]);
+                for (int j = C - 1; j >= 0; --j) {
+                    cplx L = (j == 0) ? suf : cmul(pre[j], suf);
+                    ar[j] += L.re;
+                    ai[j] += L.im;
+                    if (j > 0) { cplx cj = {cr[j], ci[j]}; suf = cmul(suf, cj); }
                 }
+                if (step == L0) break;
+                // next value of digit 0: c -= 2 * dir0 * X[0]
+                r0 += dir0;
+                sgn = -sgn;
+                const double sg = (dir0 > 0) ? -1.0 : 1.0;
+#pragma unroll
+                for (int j = 0; j < C; ++j) { cr[j] = fma(sg, x0r[j], cr[j]); ci[j] = fma(sg, x0i[j], ci[j]); }
+            }
+            dir0 = -dir0;
+            // ---- next row: one Guan step of the sub-walk over digits 1 .. D-1
+            if (++q >= row_end) break;
+            int delta;
+            const int v = guan_step(item, r, st, delta, /*v0=*/1);
+            sgn = -sgn;
+            const double sg = (delta > 0) ? -1.0 : 1.0;
+            const double2 *row = X2 + v * W + col0;
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const double2 a = row[j];
+                cr[j] = fma(sg, a.x, cr[j]);
+                ci[j] = fma(sg, a.y, ci[j]);
             }
         }
     }
@@ -221,7 +279,8 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
         } else if (first_col[v] >= 0) {
             dd re = {0.0, 0.0}, im = {0.0, 0.0};
             const double *base = a.partials + ((size_t)sample * a.chunks) * (size_t)(a.W * 4) + 4 * (int)first_col[v];
-            for (int ch = 0; ch < a.chunks; ++ch) {   // fixed chunk order
+            const int active = k3_active_chunks(a.terms[sample], a.chunks, a.groups);
+            for (int ch = 0; ch < active; ++ch) {   // fixed chunk order
                 const double *q = base + (size_t)ch * (a.W * 4);
                 dd x = {q[0], q[1]}, y = {q[2], q[3]};
                 re = dd_add(re, x);
@@ -287,7 +346,7 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-typedef void (*k3_fn)(const double *, int, const unsigned char *, const unsigned char *, const int *, int, double *);
+typedef void (*k3_fn)(const double *, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *);
 
 struct K3Variant { k3_fn fn; int lpg, c; };
 static K3Variant g_k3[4][8];   // [log2 LPG][C]
@@ -320,25 +379,29 @@ static K3Variant k3_pick(int k) {
 }
 
 int bp_k3_width(int k) { K3Variant v = k3_pick(k); return v.fn ? v.lpg * v.c : 0; }
+int bp_k3_groups(int k) { K3Variant v = k3_pick(k); return v.fn ? GW_THREADS / v.lpg : GW_THREADS; }
 
-// chunks per sample for step k over `samples` samples
+// chunk blocks launched per sample for step k over `samples` samples: sized for the collision-free
+// worst case of the walk (2^(k-2) terms) but not more than ~64 blocks per SM in total; blocks a sample
+// does not need exit immediately (k3_active_chunks).
 int bp_k3_chunks(bp_context *h, int k, long long samples) {
     if (k <= 1) return 1;
     K3Variant v = k3_pick(k);
-    const double max_terms = ldexp(1.0, k - 2);
     const int groups = GW_THREADS / (v.lpg ? v.lpg : 1);
-    long long by_work = (long long)(max_terms / (double)(groups * 48));   // >= 48 terms per group
+    const double max_terms = ldexp(1.0, k - 2);
+    long long by_work = (long long)ceil(max_terms / (double)(K3_TERMS_PER_GROUP * groups));
     if (by_work < 1) by_work = 1;
-    long long by_fill = ((long long)h->sm_count * 16 + samples - 1) / samples;   // ~4 waves of 4 blocks/SM
+    long long by_fill = ((long long)h->sm_count * 64 + samples - 1) / samples;
     if (by_fill < 1) by_fill = 1;
     long long ch = by_work < by_fill ? by_work : by_fill;
-    if (ch > 65535) ch = 65535;
+    if (ch > 256) ch = 256;
     return (int)ch;
 }
 
 // Enqueue the minors main kernel for step k (= particles in occ_s) over `samples` samples.
 int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_s, const unsigned char *d_t,
-                 const int *d_steps_total, int k, long long samples, int chunks, double *d_partials) {
+                 const int *d_steps_total, int k, long long samples, int chunks, double *d_partials,
+                 unsigned long long *d_terms) {
     if (k <= 1) return BP_OK;   // handled by the finish kernel
     K3Variant v = k3_pick(k);
     if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= 56, got %d", k);
@@ -350,7 +413,7 @@ int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_
         if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)chunks, (unsigned)samples);
-    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, m, d_s, d_t, d_steps_total, k - 1, d_partials);
+    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms);
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }

@@ -132,16 +132,19 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     if ((rc = bp_reserve(h, BP_SLOT_STATE, 2 * (size_t)m + 32))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)(W > 0 ? W : 1) * chunks))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(double) * 3 * (size_t)m))) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_MISC, 64))) return rc;
+    unsigned long long *d_terms = (unsigned long long *)h->d_buf[BP_SLOT_MISC];
     BP_CUDA(h, cudaMemcpyAsync(h->d_buf[BP_SLOT_AUX], U, ub, cudaMemcpyHostToDevice, h->stream));
     unsigned char *d_s = (unsigned char *)h->d_buf[BP_SLOT_STATE], *d_t = d_s + m;
     BP_CUDA(h, cudaMemcpyAsync(d_s, hs, 2 * (size_t)m, cudaMemcpyHostToDevice, h->stream));
     const double *dU = (const double *)h->d_buf[BP_SLOT_AUX];
     double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
-    if ((rc = bp_k3_launch(h, dU, m, d_s, d_t, nullptr, (int)k, 1, chunks, d_part))) return rc;
+    if ((rc = bp_k3_launch(h, dU, m, d_s, d_t, nullptr, (int)k, 1, chunks, d_part, d_terms))) return rc;
     double *d_min = (double *)h->d_buf[BP_SLOT_OUT], *d_pmf = d_min + 2 * (size_t)m;
     K3Finish a;
     memset(&a, 0, sizeof(a));
     a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = (int)k - 1; a.partials = d_part;
+    a.terms = d_terms; a.groups = bp_k3_groups((int)k);
     a.occ_s = d_s; a.occ_t = d_t; a.minors_out = d_min; a.pmf_out = pmf ? d_pmf : nullptr;
     if ((rc = bp_k3_finish_launch(h, a, 1))) return rc;
     double *hres = (double *)((char *)h->h_pin + ((2 * (size_t)m + 63) / 64) * 64);
@@ -202,7 +205,7 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
         if ((long long)ch * W > (long long)max_chunks * maxW) { max_chunks = ch; maxW = W; }
     }
     const size_t ub = sizeof(double) * 2 * (size_t)m * m;
-    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 8) + (size_t)m + 256;
+    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 16) + (size_t)m + 256;
     if ((rc = bp_reserve(h, BP_SLOT_AUX, ub + sizeof(double) * (size_t)(n + 2)))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_STATE, state_bytes))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_TAPE, sizeof(double) * (size_t)batch * stride))) return rc;
@@ -215,7 +218,8 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
     if (eta >= 0.0) BP_CUDA(h, cudaMemcpyAsync(d_w, weights.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     // state carve-up: ints first (alignment), then bytes
     char *base = (char *)h->d_buf[BP_SLOT_STATE];
-    int *d_nrem = (int *)base;
+    unsigned long long *d_terms = (unsigned long long *)base;
+    int *d_nrem = (int *)(d_terms + batch);
     int *d_steps = d_nrem + batch;
     unsigned char *d_occ_s = (unsigned char *)(d_steps + batch);
     unsigned char *d_occ_t = d_occ_s + (size_t)batch * m;
@@ -241,10 +245,11 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
         BP_CHECK_LAUNCH(h);
         for (int k = 1; k <= n; ++k) {
             const int chunks = bp_k3_chunks(h, k, S), W = bp_k3_width(k);
-            if ((rc = bp_k3_launch(h, dU, m, d_occ_s, d_occ_t, d_steps, k, S, chunks, d_part))) return rc;
+            if ((rc = bp_k3_launch(h, dU, m, d_occ_s, d_occ_t, d_steps, k, S, chunks, d_part, d_terms))) return rc;
             K3Finish a;
             memset(&a, 0, sizeof(a));
             a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = k - 1; a.partials = d_part;
+            a.terms = d_terms; a.groups = bp_k3_groups(k);
             a.occ_s = d_occ_s; a.occ_t = d_occ_t;
             a.tape = d_tape; a.tape_stride = stride; a.remaining = d_rem; a.n_remaining = d_nrem; a.n = n;
             a.steps_total = d_steps;
