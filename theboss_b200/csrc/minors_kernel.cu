@@ -26,6 +26,8 @@
 #include "guan_walker.cuh"
 #include "minors.cuh"
 
+#include <stdlib.h>
+
 // shuffle inside one lane group only: groups of a warp may run different trip counts
 __device__ __forceinline__ cplx cshfl_xor(unsigned gmask, cplx a, int mask) {
     cplx r;
@@ -47,6 +49,7 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
 // walk by orders of magnitude, so the grid is sized for the collision-free worst case and blocks beyond
 // `active` exit at once; the finish kernel applies the same rule.
 #define K3_TERMS_PER_GROUP 192ull
+#define K3_PMAX 512
 __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, int groups) {
     const unsigned long long per_block = K3_TERMS_PER_GROUP * (unsigned long long)groups;
     unsigned long long a = (terms + per_block - 1) / per_block;
@@ -57,7 +60,7 @@ __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int ch
 
 template <int LPG, int C>
 struct K3Cfg {
-    static constexpr int MINB = (C <= 5) ? 4 : 3;
+    static constexpr int MINB = (C <= 5) ? 4 : (C <= 7) ? 3 : 2;
 };
 
 // grid = (chunks, samples).  occ_s / occ_t: [samples][m] uint8 occupations (current input with the
@@ -80,7 +83,10 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
 
     const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
     __shared__ double bin0[BP_MAX_N + 2];      // weight table of the inner digit: C(w_0, r) (x top weight if it is the only digit)
-    __shared__ unsigned long long align_rows;  // group ranges are multiples of this many rows
+    __shared__ double blow[K3_PMAX];           // binomial product of the low digits at period position p
+    __shared__ unsigned short steptab[K3_PMAX];// transition p-1 -> p of the low digits: digit | (delta > 0) << 8
+    __shared__ int low_digits;                 // digits 1 .. low_digits are driven by the table
+    __shared__ unsigned period;                // P = prod_{v=1..low_digits} (lim_v + 1): rows per table period
     if (threadIdx.x == 0) {
         guan_item_build(item, t, m, /*inner_first=*/true);
         int c = 0;
@@ -109,28 +115,56 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
     }
     // The walk is organised in ROWS: one row = the L0 + 1 terms that differ only in digit 0 (swept up
     // on even rows, down on odd rows: reflected code); rows are indexed by the sub-walk over digits
-    // 1 .. D-1.  A lane group owns a contiguous range of rows.
+    // 1 .. D-1.  A lane group owns a contiguous range of rows that is a multiple of the PERIOD of the
+    // low digits 1 .. low_digits; inside a period the step sequence is the same for every group, so it
+    // comes from a table built once per block (reflection: odd periods run it backwards).  Only the
+    // carry into the digits above (once per period) uses the generic Guan stepper.
     const int L0 = item.lim[0];
     const unsigned long long rows = item.terms / (unsigned long long)(L0 + 1);
     const unsigned long long ngroups = (unsigned long long)active * GROUPS;
     if (threadIdx.x == 0) {
-        // align the per-group row count to the period of the low digits so that all groups of a warp
-        // take the same branches inside guan_step (the carry pattern of the low digits is then identical)
-        unsigned long long raw = (rows + ngroups - 1) / ngroups, al = 1;
+        unsigned long long raw = (rows + ngroups - 1) / ngroups, P = 1;
+        int a = 0;
         for (int v = 1; v < D; ++v) {
-            const unsigned long long nxt = al * (unsigned long long)(item.lim[v] + 1);
-            if (nxt * 4 > raw) break;
-            al = nxt;
+            const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
+            if (nxt * 16 > raw || nxt > K3_PMAX) break;
+            P = nxt; a = v;
         }
-        align_rows = al;
+        period = (unsigned)P;
+        low_digits = a;
+    }
+    __syncthreads();
+    const unsigned P = period;
+    const int a_low = low_digits;
+    for (unsigned p = threadIdx.x; p < P; p += GW_THREADS) {
+        // digits of position p and p - 1 of the reflected code over digits 1 .. a_low
+        double bprod = 1.0;
+        unsigned q = p, qm = p ? p - 1 : 0;
+        int chg = 0, up = 0;
+        for (int v = 1; v <= a_low; ++v) {
+            const unsigned R = (unsigned)item.lim[v] + 1u;
+            unsigned d = q % R; q /= R;
+            unsigned dm = qm % R; qm /= R;
+            const int rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
+            const int rm = (qm & 1u) ? (int)item.lim[v] - (int)dm : (int)dm;
+            if (p && rv != rm) { chg = v; up = rv > rm; }
+            double c = gw_binom(item.mult[v], rv);
+            if (v == D - 1) c *= gw_top_weight(item, rv);
+            bprod *= c;
+        }
+        blow[p] = bprod;
+        steptab[p] = (unsigned short)(chg | (up << 8));
     }
     __syncthreads();
 
     const int lane_in_group = threadIdx.x % LPG, group = threadIdx.x / LPG;
-    unsigned long long rspan = (rows + ngroups - 1) / ngroups;
-    rspan = (rspan + align_rows - 1) / align_rows * align_rows;
-    if (rspan < 1) rspan = 1;
-    const unsigned long long row_start = ((unsigned long long)chunk * GROUPS + group) * rspan;
+    // whole periods are dealt out to the lane groups; counts differ by at most one period
+    const unsigned long long nper = rows / P;                     // rows is a multiple of P
+    const unsigned long long gidx = (unsigned long long)chunk * GROUPS + group;
+    const unsigned long long pbase = nper / ngroups, prem = nper % ngroups;
+    const unsigned long long my_periods = pbase + (gidx < prem ? 1ull : 0ull);
+    const unsigned long long row_start = (gidx * pbase + (gidx < prem ? gidx : prem)) * P;
+    const unsigned long long rspan = my_periods * P;
     const int col0 = lane_in_group * C;
     const unsigned gmask = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << ((threadIdx.x & 31) / LPG * LPG));
 
@@ -140,37 +174,51 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
 
     // loop bounds are uniform inside a lane group and the shuffles are masked to the group, so
     // groups of one warp may run different trip counts.
-    if (row_start < rows) {
-        const unsigned long long row_end = (rows - row_start < rspan) ? rows : row_start + rspan;
+    if (my_periods > 0) {
+        const unsigned long long row_end = row_start + rspan;
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
-        guan_seek(item, row_start, r, st, /*v0=*/1);
-        int r0 = (row_start & 1ull) ? L0 : 0;          // reflected: odd rows sweep digit 0 downwards
+        const unsigned long long hi0 = row_start / P;       // row_start is a multiple of P
+        guan_seek(item, hi0, r, st, /*v0=*/a_low + 1);      // digits above the table
+        int pos = (hi0 & 1ull) ? (int)P - 1 : 0;            // position inside the period (reflected)
+        int pdir = (hi0 & 1ull) ? -1 : 1;
+        unsigned off = 0;                                    // rows done in the current period
+        int r0 = (row_start & 1ull) ? L0 : 0;               // reflected: odd rows sweep digit 0 downwards
         int dir0 = (row_start & 1ull) ? -1 : 1;
         double cr[C], ci[C], x0r[C], x0i[C];
 #pragma unroll
         for (int j = 0; j < C; ++j) { cr[j] = 0.0; ci[j] = 0.0; }
-        int par = r0;                                   // parity of sum(rho) -> sign of the term
+        int par = r0;                                        // parity of sum(rho) -> sign of the term
+        {
+            unsigned q = (unsigned)pos;
 #pragma unroll 1
-        for (int v = 0; v < D; ++v) {
-            const int rv = (v == 0) ? r0 : (int)r[v * GW_THREADS];
-            if (v > 0) par += rv;
-            const double coef = 0.5 * (double)((int)item.mult[v] - 2 * rv);
-            const double2 *row = X2 + v * W + col0;
+            for (int v = 0; v < D; ++v) {
+                int rv;
+                if (v == 0) rv = r0;
+                else if (v <= a_low) {
+                    const unsigned R = (unsigned)item.lim[v] + 1u;
+                    const unsigned d = q % R; q /= R;
+                    rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
+                } else rv = (int)r[v * GW_THREADS];
+                if (v > 0) par += rv;
+                const double coef = 0.5 * (double)((int)item.mult[v] - 2 * rv);
+                const double2 *row = X2 + v * W + col0;
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                const double2 a = row[j];
-                cr[j] = fma(coef, a.x, cr[j]);
-                ci[j] = fma(coef, a.y, ci[j]);
+                for (int j = 0; j < C; ++j) {
+                    const double2 a = row[j];
+                    cr[j] = fma(coef, a.x, cr[j]);
+                    ci[j] = fma(coef, a.y, ci[j]);
+                }
             }
         }
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            const double2 a = X2[col0 + j];             // row of digit 0, kept in registers
+            const double2 a = X2[col0 + j];                  // row of digit 0, kept in registers
             x0r[j] = a.x; x0i[j] = a.y;
             if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
         }
         double sgn = (par & 1) ? -1.0 : 1.0;
+        double bout = st.binom * blow[pos];                  // binomial product of digits 1 .. D-1
 
 #pragma unroll 1
         for (unsigned long long q = row_start;;) {
@@ -197,7 +245,7 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
                         if ((mask << 1) < LPG) all = cmul(all, x);
                     }
                 }
-                const double w = sgn * st.binom * bin0[r0];
+                const double w = sgn * bout * bin0[r0];
                 cplx suf = {w * oth.re, w * oth.im};
                 // suffix pass: leave-one-out products, accumulate
 #pragma unroll
@@ -216,12 +264,28 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
                 for (int j = 0; j < C; ++j) { cr[j] = fma(sg, x0r[j], cr[j]); ci[j] = fma(sg, x0i[j], ci[j]); }
             }
             dir0 = -dir0;
-            // ---- next row: one Guan step of the sub-walk over digits 1 .. D-1
+            // ---- next row
             if (++q >= row_end) break;
-            int delta;
-            const int v = guan_step(item, r, st, delta, /*v0=*/1);
+            int v, up;
+            if (++off < P) {
+                // table step of the low digits (same for every group of the block)
+                const int idx = (pdir > 0) ? pos + 1 : pos;
+                const unsigned e = steptab[idx];
+                v = (int)(e & 0xffu);
+                up = (pdir > 0) ? (int)(e >> 8) : 1 - (int)(e >> 8);
+                pos += pdir;
+                bout = st.binom * blow[pos];
+            } else {
+                // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
+                int delta;
+                v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+                up = delta > 0;
+                off = 0;
+                pdir = -pdir;
+                bout = st.binom * blow[pos];
+            }
             sgn = -sgn;
-            const double sg = (delta > 0) ? -1.0 : 1.0;
+            const double sg = up ? -1.0 : 1.0;               // c -= 2 * delta * X[v]
             const double2 *row = X2 + v * W + col0;
 #pragma unroll
             for (int j = 0; j < C; ++j) {
@@ -349,7 +413,8 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
 typedef void (*k3_fn)(const double *, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *);
 
 struct K3Variant { k3_fn fn; int lpg, c; };
-static K3Variant g_k3[4][8];   // [log2 LPG][C]
+#define K3_MAX_C 12
+static K3Variant g_k3[4][K3_MAX_C + 1];   // [log2 LPG][C]
 static bool g_k3_init = false;
 
 template <int LPG, int C>
@@ -361,17 +426,28 @@ static void k3_reg(int lg) {
 template <int LPG>
 static void k3_reg_all(int lg) {
     k3_reg<LPG, 1>(lg); k3_reg<LPG, 2>(lg); k3_reg<LPG, 3>(lg); k3_reg<LPG, 4>(lg);
-    k3_reg<LPG, 5>(lg); k3_reg<LPG, 6>(lg); k3_reg<LPG, 7>(lg);
+    k3_reg<LPG, 5>(lg); k3_reg<LPG, 6>(lg); k3_reg<LPG, 7>(lg); k3_reg<LPG, 8>(lg);
+    k3_reg<LPG, 9>(lg); k3_reg<LPG, 10>(lg); k3_reg<LPG, 11>(lg); k3_reg<LPG, 12>(lg);
 }
 
-// Smallest padded width LPG * C >= k with C <= 7, preferring fewer lanes per group.
+// Variant for k input columns: smallest padded width LPG * C >= k with C <= max_c, preferring fewer
+// lanes per group.  max_c defaults to K3_DEFAULT_MAX_C; BP_K3_MAX_C overrides it (tuning).
+#define K3_DEFAULT_MAX_C 8
 static K3Variant k3_pick(int k) {
-    if (!g_k3_init) { k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3); g_k3_init = true; }
+    static int max_c = 0;
+    if (!g_k3_init) {
+        k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3);
+        const char *e = getenv("BP_K3_MAX_C");
+        max_c = e ? atoi(e) : K3_DEFAULT_MAX_C;
+        if (max_c < 7) max_c = 7;
+        if (max_c > K3_MAX_C) max_c = K3_MAX_C;
+        g_k3_init = true;
+    }
     int best_lg = -1, best_c = 0, best_w = 1 << 30;
     for (int lg = 0; lg < 4; ++lg) {
         const int lpg = 1 << lg;
         const int c = (k + lpg - 1) / lpg;
-        if (c > 7) continue;
+        if (c > max_c) continue;
         if (lpg * c < best_w) { best_w = lpg * c; best_lg = lg; best_c = c; }
     }
     K3Variant none = {nullptr, 0, 0};
@@ -404,7 +480,7 @@ int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_
                  unsigned long long *d_terms) {
     if (k <= 1) return BP_OK;   // handled by the finish kernel
     K3Variant v = k3_pick(k);
-    if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= 56, got %d", k);
+    if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= %d, got %d", 8 * K3_DEFAULT_MAX_C, k);
     if (k - 1 > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k - 1 <= %d, got k = %d", BP_MAX_N, k);
     if (samples > 65535) return bp_fail(h, BP_ERR_INVALID, "bp_k3_launch: at most 65535 samples per launch");
     const size_t smem = k3_smem_bytes(k - 1, v.lpg * v.c, v.c);
