@@ -143,3 +143,29 @@ class ShardedGlynnPermanent:
     @property
     def d2h_bytes(self) -> int:
         return 32 * self.world_size
+
+
+def sharded_gccb_simulate(U, input_state, n_samples: int, eta: float = -1.0, seed: int = 0, device: Optional[int] = None,
+                          group=None, gather: bool = True):
+    """GCC-B sampling run split over the ranks of a process group: rank r draws the contiguous slice
+    ``shard_bounds(n_samples, world, r)`` of the samples with the counter-based generator keyed by the GLOBAL
+    sample index (``first_sample``), so the concatenation equals the single-GPU run bit for bit.  No traffic
+    until the final gather.  Returns an (n_samples, m) int32 array on every rank
+    (or only this rank's slice with ``gather=False``)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _native
+
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    dev = torch.cuda.current_device() if device is None else int(device)
+    lo, hi = shard_bounds(n_samples, world, rank)
+    Um = _native.as_matrix(U)
+    s = _native.as_state(input_state, Um.shape[0])
+    local = _native.default_handle(dev).gccb_simulate(Um, s, hi - lo, eta=eta, seed=seed, first_sample=lo)
+    if not gather or world == 1:
+        return local
+    t = torch.from_numpy(local).to(torch.device("cuda", dev))
+    return gather_samples(t, group).cpu().numpy()
