@@ -187,31 +187,64 @@ def secondary_metrics(device):
             ts.append(time.perf_counter() - t0)
         return min(ts)
 
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+
+    def cpu_parallel(fn, jobs):
+        """Runs fn(job) for every job on all host cores (ctypes releases the GIL inside the oracle)."""
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(fn, jobs))
+        return time.perf_counter() - t0
+
     try:   # C2: 10^4 batched n=20 permanents with repeated rows and columns
+        from oracle import pyoracle as orc
         U, S, T = workloads.c2_batch(items=10_000)
         t = best_of(lambda: h.perm_batched(U, S, T))
         terms = 0.0
         for b in range(S.shape[0]):
             cs = np.prod(S[b].astype(np.float64) + 1) ; ct = np.prod(T[b].astype(np.float64) + 1)
             terms += min(cs, ct) / 2
+        sub = min(10_000, 4 * cores)
+        tc = cpu_parallel(lambda b: orc.guan_permanent(U, S[b], T[b], orc.CHIN_HUH, "d"), range(sub))
         out["c2_batched_n20_m40"] = {"items": 10_000, "seconds": t, "permanents_per_s": 10_000 / t,
-                                     "approx_useful_tflops": terms * (6 * 20 + 6 * 19 + 4) / t / 1e12}
+                                     "approx_useful_tflops": terms * (6 * 20 + 6 * 19 + 4) / t / 1e12,
+                                     "cpu_port": {"permanents_per_s": sub / tc, "cores": cores,
+                                                  "sample": f"first {sub} items, oracle Chin-Huh double (reference algorithm: walks the input side, no symmetry halving)"}}
     except Exception as e:   # noqa: BLE001
         out["c2_batched_n20_m40"] = {"error": repr(e)}
     try:   # C3: one GCC-B step at n=24, m=48 (all 24 minors + 48 probabilities)
+        from oracle import pyoracle as orc
         for name, cf in (("c3_step_n24_m48_bunched_outputs", False), ("c3_step_n24_m48_collision_free", True)):
             U, s, tt = workloads.c3_step(24, 48, cf)
             t = best_of(lambda: h.gccb_pmf(U, s, tt))
             T_terms = np.prod(tt.astype(np.float64) + 1) / 2
             out[name] = {"seconds": t, "steps_per_s": 1 / t, "useful_tflops": T_terms * (22 * 24 - 36) / t / 1e12}
+        U, s, tt = workloads.c3_step(24, 48, False)
+        tc = cpu_parallel(lambda _: orc.gccb_pmf(U, s, tt, "d"), range(cores))
+        out["c3_step_n24_m48_bunched_outputs"]["cpu_port"] = {
+            "steps_per_s": cores / tc, "cores": cores,
+            "sample": f"{cores} concurrent evaluations of the same step, oracle sub-Ryser double (2^24 Guan terms each, the reference's algorithm)"}
     except Exception as e:   # noqa: BLE001
         out["c3_step_n24_m48"] = {"error": repr(e)}
     try:   # GCC-B sampling run at n=24, m=48
+        from oracle import pyoracle as orc
         U = workloads.haar(48, 24)
         s = np.array([1] * 24 + [0] * 24, dtype=np.int32)
-        S_n = 512
+        S_n = 4096
         t = best_of(lambda: h.gccb_simulate(U, s, S_n, seed=5), reps=2)
         out["gccb_n24_m48"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t}
+        n_cpu = 20   # the reference algorithm needs sum_k 2^k Guan terms per sample: run a smaller n on the CPU
+        Uc = workloads.haar(2 * n_cpu, n_cpu)
+        sc = np.array([1] * n_cpu + [0] * n_cpu, dtype=np.int32)
+        tapes = np.random.RandomState(3).random_sample((cores, 1, 1 + 2 * n_cpu))
+        tc = cpu_parallel(lambda i: orc.gccb_simulate(Uc, sc, tapes[i]), range(cores))
+        out["gccb_n24_m48"]["cpu_port"] = {
+            "samples_per_s_at_n20": cores / tc, "cores": cores,
+            "samples_per_s_extrapolated_to_n24": cores / tc / 2.0 ** 4,
+            "sample": f"{cores} samples at n=20, m=40 (oracle sampling loop, double); cost per sample doubles with every photon, so n=24 is 2^4 times slower"}
+        tg = best_of(lambda: h.gccb_simulate(Uc, sc, 16384, seed=5), reps=2)
+        out["gccb_n20_m40"] = {"samples": 16384, "seconds": tg, "samples_per_s": 16384 / tg}
     except Exception as e:   # noqa: BLE001
         out["gccb_n24_m48"] = {"error": repr(e)}
     try:   # C5 (i): uniform losses eta = 0.5, n=30, m=60
