@@ -4,11 +4,14 @@
 * ``mode_occupation_to_mode_assignment``                 (:61-78)
 * ``prepare_interferometer_matrix_in_expanded_space``    (:287-342, helper :263-284)
 * ``EffectiveScatteringMatrixCalculator``                (:545-626)
+* ``generate_possible_states`` / ``generate_lossy_n_particle_input_states`` (:81-203), needed by the exact
+  distribution calculators that sit on top of the batched permanent kernel
 
 The expansion of rows/columns by occupation is done on the device inside the kernels
 (theboss_b200/csrc/util_kernels.cu, guan_kernel.cu); the class below exists for API compatibility and
 for callers that want the explicit matrix.
 """
+import itertools
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -18,6 +21,57 @@ def mode_occupation_to_mode_assignment(mode_occupation: Sequence[int]) -> Tuple[
     """2nd-quantisation occupation -> 1st-quantisation list of modes, e.g. [2,0,1] -> (0,0,2)."""
     occ = np.asarray(mode_occupation).astype(np.int64)
     return tuple(int(v) for v in np.repeat(np.arange(len(occ)), occ))
+
+
+def mode_assignment_to_mode_occupation(modes_assignment: Sequence[int], observed_modes_number: int = 0) -> Tuple[int, ...]:
+    """1st-quantisation list of modes -> occupation vector, e.g. (0,0,2), 4 -> (2,0,1,0)."""
+    modes = [int(v) for v in modes_assignment]
+    size = max(observed_modes_number, (max(modes) + 1) if modes else 0)
+    occ = [0] * size
+    for v in modes:
+        occ[v] += 1
+    return tuple(occ)
+
+
+def _n_particle_states(n: int, modes_number: int) -> List[Tuple[int, ...]]:
+    """All occupations of ``modes_number`` modes by exactly n particles, in descending lexicographic order
+    (the order of the reference's generate_possible_states, :117-155)."""
+    if modes_number == 1:
+        return [(n,)]
+    out = []
+    for first in range(n, -1, -1):
+        out.extend((first,) + rest for rest in _n_particle_states(n - first, modes_number - 1))
+    return out
+
+
+def generate_possible_states(particles_number: int, modes_number: int, losses: bool = False) -> List[Tuple[int, ...]]:
+    """All m-mode states with exactly n particles, or (``losses=True``) with 0..n particles ordered by
+    particle number; every block in descending lexicographic order."""
+    if particles_number < 0 or modes_number < 1:
+        return []
+    if particles_number == 0:
+        return [tuple([0] * modes_number)]
+    first = 0 if losses else particles_number
+    states: List[Tuple[int, ...]] = []
+    for n in range(first, particles_number + 1):
+        states.extend(_n_particle_states(n, modes_number))
+    return states
+
+
+def generate_lossy_n_particle_input_states(initial_state: Sequence[int], number_of_particles_left: int) -> List[Tuple[int, ...]]:
+    """Distinct occupations obtained by keeping ``number_of_particles_left`` of the input particles, in
+    order of first appearance over itertools.combinations of the particle list (reference :158-203)."""
+    if sum(initial_state) == 0:
+        return [tuple(initial_state)]
+    m = len(initial_state)
+    particles = mode_occupation_to_mode_assignment(initial_state)
+    seen, out = set(), []
+    for combo in itertools.combinations(particles, number_of_particles_left):
+        occ = mode_assignment_to_mode_occupation(combo, m)
+        if occ not in seen:
+            seen.add(occ)
+            out.append(occ)
+    return out
 
 
 def prepare_interferometer_matrix_in_expanded_space(interferometer_matrix) -> np.ndarray:

@@ -10,10 +10,10 @@ Like the reference the factory deep-copies the calculator it is given (:58, :107
 import enum
 from copy import deepcopy
 
-from .generalized_cliffords_b_uniform_losses_simulation_strategy import (
-    GeneralizedCliffordsBUniformLossesSimulationStrategy,
-)
 from .generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy
+from .generalized_cliffords_uniform_losses_simulation_strategy import (
+    GeneralizedCliffordsUniformLossesSimulationStrategy,
+)
 from .lossy_networks_generalized_cliffords_simulation_strategy import (
     LossyNetworksGeneralizedCliffordsSimulationStrategy,
 )
@@ -65,9 +65,8 @@ class SimulationStrategyFactory:
         if kind == StrategyType.LOSSY_NET_GCC:
             return LossyNetworksGeneralizedCliffordsSimulationStrategy(calc)
         if kind == StrategyType.UNIFORM_LOSSES_GCC:
-            # The reference maps this member to the version-A sampler with per-particle Bernoulli losses;
-            # the same output distribution is produced by GCC-B after a Binomial(n, eta) particle-number draw.
-            return GeneralizedCliffordsBUniformLossesSimulationStrategy(
+            # simulation_strategy_factory.py:175-181 of the reference: version A with per-particle Bernoulli losses
+            return GeneralizedCliffordsUniformLossesSimulationStrategy(
                 calc, getattr(self.experiment_configuration, "uniform_transmissivity", 1.0))
         raise NotImplementedError(
             f"{kind.name} is outside the permanent hot path built here; use the reference class {_OUT_OF_SCOPE.get(kind)}")
