@@ -12,3 +12,6 @@ cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:glynn_block4_kernel -s 1 -c 1 -f -o gpurun_out/k1_n30 python scripts/profile_k1.py 30 > gpurun_out/ncu_k1.log 2>&1
 tail -3 gpurun_out/ncu_k1.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k3_minors_kernel -s 22 -c 1 -f -o gpurun_out/k3_n24 python scripts/profile_k3.py 24 2048 0 > gpurun_out/ncu_k3.log 2>&1
+tail -2 gpurun_out/ncu_k3.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/k3_launches.csv python scripts/profile_k3.py 24 4096 0 > /dev/null 2>&1
