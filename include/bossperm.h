@@ -151,6 +151,17 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
                      double eta, uint64_t seed, int64_t first_sample, const double *tape,
                      int32_t *out);
 
+/* One interferometer AND one input state per sample: what the BOBS strategies need, which draw fresh
+ * random phases (a new matrix) and a fresh lossy input state for every sample and then take ONE GCC-B sample
+ * (simulation_strategies/nonuniform_losses_approximation_strategy.py:263-296,
+ *  simulation_strategies/lossy_state_approximated_simulation_strategy.py:287-310).
+ *   Us:     n_samples x m x m complex, states: n_samples x m occupations (particle numbers may differ).
+ *   tape:   NULL (Philox as above) or n_samples x (1 + 2 * tape_particles) uniforms,
+ *           tape_particles >= the largest particle number of any sample. */
+int bp_gccb_simulate_batch(bp_handle h, const double *Us, int m, const int32_t *states, int64_t n_samples,
+                           uint64_t seed, int64_t first_sample, const double *tape, int tape_particles,
+                           int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

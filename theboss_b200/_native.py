@@ -54,6 +54,7 @@ SIGNATURES = {
     "bp_minors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bp_gccb_pmf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bp_gccb_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "bp_gccb_simulate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 _lib = None
@@ -224,6 +225,27 @@ class Handle:
             tp = tape.ctypes.data
         self._check(self._lib.bp_gccb_simulate(self._h, U.ctypes.data, m, s.ctypes.data, int(n_samples), float(eta),
                                                int(seed) & (2 ** 64 - 1), int(first_sample), tp, out.ctypes.data))
+        return out
+
+
+    def gccb_simulate_batch(self, Us: np.ndarray, states: np.ndarray, seed: int = 0, first_sample: int = 0,
+                            tape: Optional[np.ndarray] = None) -> np.ndarray:
+        """One GCC-B sample per (matrix, input state) pair: Us (S, m, m) complex128, states (S, m) ints."""
+        Us = np.ascontiguousarray(Us, dtype=np.complex128)
+        states = np.ascontiguousarray(states, dtype=np.int32)
+        if Us.ndim != 3 or Us.shape[1] != Us.shape[2] or states.shape != Us.shape[:2]:
+            raise AttributeError("Us must be (S, m, m) and states (S, m)")
+        S, m = states.shape
+        out = np.zeros((S, m), dtype=np.int32)
+        tp, tn = None, 0
+        if tape is not None:
+            tape = np.ascontiguousarray(tape, dtype=np.float64)
+            tn = (tape.shape[1] - 1) // 2
+            if tape.shape[0] != S or tape.shape[1] != 1 + 2 * tn or tn < int(states.sum(axis=1).max(initial=0)):
+                raise ValueError("decision tape must have shape (S, 1 + 2 * n_max)")
+            tp = tape.ctypes.data
+        self._check(self._lib.bp_gccb_simulate_batch(self._h, Us.ctypes.data, m, states.ctypes.data, S, int(seed) & (2 ** 64 - 1),
+                                                     int(first_sample), tp, tn, out.ctypes.data))
         return out
 
 

@@ -104,3 +104,26 @@ class EffectiveScatteringMatrixCalculator:
         cols = list(mode_occupation_to_mode_assignment(self.input_state))
         rows = list(mode_occupation_to_mode_assignment(self.output_state))
         return list(U[np.ix_(rows, cols)])
+
+
+def compute_qft_matrix(n: int) -> np.ndarray:
+    """n x n quantum Fourier transform, omega^(jk) / sqrt(n) (reference: quantum_computations_utilities.py:159-178)."""
+    if n == 0:
+        return np.asarray([])
+    k = np.arange(n)
+    return np.power(np.exp(2j * np.pi / n), np.outer(k, k)) / np.sqrt(n)
+
+
+def generate_qft_matrix_for_first_m_modes(m: int, all_modes_number: int) -> np.ndarray:
+    """QFT on the first m modes, identity on the rest (reference :505-522)."""
+    out = np.eye(all_modes_number, dtype=np.complex128)
+    if m > 0:
+        out[:m, :m] = compute_qft_matrix(m)
+    return out
+
+
+def generate_random_phases_matrix_for_first_m_modes(m: int, all_modes_number: int) -> np.ndarray:
+    """diag(e^{2 pi i u_1}, ..., e^{2 pi i u_m}, 1, ..., 1) with u ~ numpy.random.rand(m) (reference :525-543)."""
+    phases = np.ones(all_modes_number, dtype=np.complex128)
+    phases[:m] = np.exp(1j * 2 * np.pi * np.random.rand(m))
+    return np.diag(phases)

@@ -3,7 +3,8 @@
 #include "bp_common.cuh"
 
 struct K3Finish {
-    const double *U; int m; int W; int chunks; int step;       // step = k - 1 (0-based)
+    const double *U; size_t u_stride;                          // per-sample matrix stride in doubles (0 = shared)
+    int m; int W; int chunks; int step;                        // step = k - 1 (0-based)
     const double *partials;
     const unsigned long long *terms; int groups;               // per-sample walk length (written by K3), lane groups per block
     unsigned char *occ_s, *occ_t;                              // [samples][m]
@@ -18,7 +19,7 @@ struct K3Finish {
 int bp_k3_width(int k);
 int bp_k3_chunks(bp_context *h, int k, long long samples);
 int bp_k3_groups(int k);
-int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_s, const unsigned char *d_t,
+int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const unsigned char *d_s, const unsigned char *d_t,
                  const int *d_steps_total, int k, long long samples, int chunks, double *d_partials,
                  unsigned long long *d_terms);
 int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples);

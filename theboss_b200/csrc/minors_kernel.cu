@@ -68,7 +68,7 @@ struct K3Cfg {
 // partials: [samples][chunks][LPG*C][4] double-double partial sums.
 template <int LPG, int C>
 __global__ void __launch_bounds__(GW_THREADS, K3Cfg<LPG, C>::MINB)
-k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ occ_s,
+k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const unsigned char *__restrict__ occ_s,
                  const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, int step,
                  double *__restrict__ partials, unsigned long long *__restrict__ terms_out) {
     constexpr int W = LPG * C;
@@ -78,6 +78,7 @@ k3_minors_kernel(const double *__restrict__ U, int m, const unsigned char *__res
     __shared__ short col_mode[W];
 
     const int sample = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const double *U = U0 + (size_t)sample * u_stride;   // u_stride = 0: one interferometer for all samples
     double *my_part = partials + ((size_t)sample * chunks + chunk) * (size_t)(W * 4);
     if (steps_total && step >= steps_total[sample]) return;   // uniform-loss variant: this sample is complete
 
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
     }
     __syncthreads();
     if (!a.pmf_out && !a.tape) return;
-    const double2 *U2 = reinterpret_cast<const double2 *>(a.U);
+    const double2 *U2 = reinterpret_cast<const double2 *>(a.U + (size_t)sample * a.u_stride);
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         double re = 0.0, im = 0.0;
         for (int i = 0; i < m; ++i) {
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-typedef void (*k3_fn)(const double *, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *);
+typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *);
 
 struct K3Variant { k3_fn fn; int lpg, c; };
 #define K3_MAX_C 12
@@ -475,7 +476,7 @@ int bp_k3_chunks(bp_context *h, int k, long long samples) {
 }
 
 // Enqueue the minors main kernel for step k (= particles in occ_s) over `samples` samples.
-int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_s, const unsigned char *d_t,
+int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const unsigned char *d_s, const unsigned char *d_t,
                  const int *d_steps_total, int k, long long samples, int chunks, double *d_partials,
                  unsigned long long *d_terms) {
     if (k <= 1) return BP_OK;   // handled by the finish kernel
@@ -489,7 +490,7 @@ int bp_k3_launch(bp_context *h, const double *dU, int m, const unsigned char *d_
         if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)chunks, (unsigned)samples);
-    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms);
+    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms);
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }

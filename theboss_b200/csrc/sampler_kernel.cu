@@ -53,7 +53,7 @@ __global__ void k4_fill_tape_kernel(double *__restrict__ tape, long long samples
 // One thread per sample: particle number (uniform-loss inverse CDF,
 // generalized_cliffords_b_uniform_losses_simulation_strategy.py:67-85), remaining-particle list
 // (mode assignment, boson_sampling_utilities.py:61-78), empty states, and the first input particle.
-__global__ void k4_init_kernel(const unsigned char *__restrict__ s0, int m, int n, const double *__restrict__ loss_weights,
+__global__ void k4_init_kernel(const unsigned char *__restrict__ s0_base, size_t s0_stride, int m, int n, const double *__restrict__ loss_weights,
                                const double *__restrict__ tape, int tape_stride, long long samples,
                                unsigned char *__restrict__ occ_s, unsigned char *__restrict__ occ_t,
                                unsigned char *__restrict__ remaining, int *__restrict__ n_remaining,
@@ -61,7 +61,10 @@ __global__ void k4_init_kernel(const unsigned char *__restrict__ s0, int m, int 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= samples) return;
     const double *tp = tape + i * tape_stride;
-    int steps = n;
+    const unsigned char *s0 = s0_base + (size_t)i * s0_stride;   // s0_stride = 0: one input state for all samples
+    int steps = 0;
+    for (int v = 0; v < m; ++v) steps += s0[v];                   // particles of THIS sample (<= n)
+    const int n_mine = steps;
     if (loss_weights) {
         steps = 0;
         double run = 0.0;
@@ -80,7 +83,7 @@ __global__ void k4_init_kernel(const unsigned char *__restrict__ s0, int m, int 
     int c = 0;
     for (int v = 0; v < m; ++v)
         for (int a = 0; a < s0[v]; ++a) rem[c++] = (unsigned char)v;
-    int nr = n;
+    int nr = n_mine;
     if (steps > 0) {
         int pick = (int)(tp[1] * (double)nr);
         if (pick >= nr) pick = nr - 1;
@@ -139,7 +142,7 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     BP_CUDA(h, cudaMemcpyAsync(d_s, hs, 2 * (size_t)m, cudaMemcpyHostToDevice, h->stream));
     const double *dU = (const double *)h->d_buf[BP_SLOT_AUX];
     double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
-    if ((rc = bp_k3_launch(h, dU, m, d_s, d_t, nullptr, (int)k, 1, chunks, d_part, d_terms))) return rc;
+    if ((rc = bp_k3_launch(h, dU, 0, m, d_s, d_t, nullptr, (int)k, 1, chunks, d_part, d_terms))) return rc;
     double *d_min = (double *)h->d_buf[BP_SLOT_OUT], *d_pmf = d_min + 2 * (size_t)m;
     K3Finish a;
     memset(&a, 0, sizeof(a));
@@ -168,24 +171,33 @@ int bp_gccb_pmf(bp_handle h, const double *U, int m, const int32_t *s, const int
     return minors_host(h, U, m, s, t, minors_out, pmf, "bp_gccb_pmf");
 }
 
-int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int64_t n_samples, double eta, uint64_t seed,
-                     int64_t first_sample, const double *tape, int32_t *out) {
-    if (!h || !U || !s || !out) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate: NULL argument");
-    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_gccb_simulate: m=%d outside [1, %d]", m, BP_MAX_MODES);
-    if (n_samples < 0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate: n_samples=%lld", (long long)n_samples);
-    if (eta > 1.0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate: eta=%g > 1", eta);
+// Shared implementation.  per_sample = false: one matrix U (m x m) and one input state s for all samples;
+// per_sample = true: U is [n_samples][m][m] and s is [n_samples][m] (row f1 of SURVEY.md section 8f: the
+// BOBS strategies draw a new matrix and a new lossy input state for every sample).
+static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32_t *s, bool per_sample, int64_t n_samples,
+                              double eta, uint64_t seed, int64_t first_sample, const double *tape, int tape_n,
+                              int32_t *out, const char *who) {
+    if (!h || !U || !s || !out) return bp_fail(h, BP_ERR_INVALID, "%s: NULL argument", who);
+    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: m=%d outside [1, %d]", who, m, BP_MAX_MODES);
+    if (n_samples < 0) return bp_fail(h, BP_ERR_INVALID, "%s: n_samples=%lld", who, (long long)n_samples);
+    if (eta > 1.0) return bp_fail(h, BP_ERR_INVALID, "%s: eta=%g > 1", who, eta);
     if (n_samples == 0) return BP_OK;
     BP_CUDA(h, cudaSetDevice(h->device));
-    std::vector<unsigned char> s8((size_t)m);
-    long nl = 0;
-    int rc;
-    if ((rc = occ_to_u8(h, s, m, s8.data(), &nl, "bp_gccb_simulate"))) return rc;
-    const int n = (int)nl;
+    const size_t n_states = per_sample ? (size_t)n_samples : 1;
+    std::vector<unsigned char> s8(n_states * (size_t)m);
+    int rc, n = 0;
+    for (size_t i = 0; i < n_states; ++i) {
+        long nl = 0;
+        if ((rc = occ_to_u8(h, s + i * m, m, s8.data() + i * m, &nl, who))) return rc;
+        if ((int)nl > n) n = (int)nl;
+    }
+    if (tape_n > n) n = tape_n;   // the caller's tape may be laid out for more particles than any sample holds
     if (n == 0) { memset(out, 0, sizeof(int32_t) * (size_t)n_samples * m); return BP_OK; }
-    if (n - 1 > BP_MAX_N || bp_k3_width(n) == 0) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_gccb_simulate: n=%d too large", n);
+    if (n - 1 > BP_MAX_N || bp_k3_width(n) == 0) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: n=%d too large", who, n);
     const int stride = 1 + 2 * n;
 
-    // binomial weights C(n,l) eta^l (1-eta)^(n-l), same expression as the reference (:62-65)
+    // binomial weights C(n,l) eta^l (1-eta)^(n-l), same expression as the reference
+    // (generalized_cliffords_b_uniform_losses_simulation_strategy.py:62-65)
     std::vector<double> weights;
     if (eta >= 0.0) {
         weights.resize(n + 1);
@@ -197,26 +209,32 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
         }
     }
 
-    const long long batch_cap = 32768;
+    const size_t ub = sizeof(double) * 2 * (size_t)m * m;
+    long long batch_cap = 32768;
+    if (per_sample) {   // keep the per-batch matrix upload below ~1 GiB
+        long long by_mem = (long long)((1ull << 30) / ub);
+        if (by_mem < 1) by_mem = 1;
+        if (by_mem < batch_cap) batch_cap = by_mem;
+    }
     const long long batch = n_samples < batch_cap ? n_samples : batch_cap;
     int max_chunks = 1, maxW = 1;
     for (int k = 2; k <= n; ++k) {
         const int ch = bp_k3_chunks(h, k, batch), W = bp_k3_width(k);
         if ((long long)ch * W > (long long)max_chunks * maxW) { max_chunks = ch; maxW = W; }
     }
-    const size_t ub = sizeof(double) * 2 * (size_t)m * m;
-    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 16) + (size_t)m + 256;
-    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub + sizeof(double) * (size_t)(n + 2)))) return rc;
+    const size_t u_count = per_sample ? (size_t)batch : 1;
+    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 16) + u_count * (size_t)m + (size_t)m + 256;
+    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub * u_count + sizeof(double) * (size_t)(n + 2)))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_STATE, state_bytes))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_TAPE, sizeof(double) * (size_t)batch * stride))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)maxW * max_chunks * (size_t)batch))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(int) * (size_t)batch * m))) return rc;
 
     double *dU = (double *)h->d_buf[BP_SLOT_AUX];
-    double *d_w = dU + 2 * (size_t)m * m;
-    BP_CUDA(h, cudaMemcpyAsync(dU, U, ub, cudaMemcpyHostToDevice, h->stream));
+    double *d_w = dU + 2 * (size_t)m * m * u_count;
+    if (!per_sample) BP_CUDA(h, cudaMemcpyAsync(dU, U, ub, cudaMemcpyHostToDevice, h->stream));
     if (eta >= 0.0) BP_CUDA(h, cudaMemcpyAsync(d_w, weights.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, h->stream));
-    // state carve-up: ints first (alignment), then bytes
+    // state carve-up: 8-byte and 4-byte items first (alignment), then bytes
     char *base = (char *)h->d_buf[BP_SLOT_STATE];
     unsigned long long *d_terms = (unsigned long long *)base;
     int *d_nrem = (int *)(d_terms + batch);
@@ -225,13 +243,18 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
     unsigned char *d_occ_t = d_occ_s + (size_t)batch * m;
     unsigned char *d_rem = d_occ_t + (size_t)batch * m;
     unsigned char *d_s0 = d_rem + (size_t)batch * n;
-    BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data(), (size_t)m, cudaMemcpyHostToDevice, h->stream));
+    if (!per_sample) BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data(), (size_t)m, cudaMemcpyHostToDevice, h->stream));
     double *d_tape = (double *)h->d_buf[BP_SLOT_TAPE];
     double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
     int *d_out = (int *)h->d_buf[BP_SLOT_OUT];
+    const size_t u_stride = per_sample ? 2 * (size_t)m * m : 0, s0_stride = per_sample ? (size_t)m : 0;
 
     for (long long done = 0; done < n_samples; done += batch) {
         const long long S = (n_samples - done < batch) ? (n_samples - done) : batch;
+        if (per_sample) {
+            BP_CUDA(h, cudaMemcpyAsync(dU, U + (size_t)done * 2 * m * m, ub * (size_t)S, cudaMemcpyHostToDevice, h->stream));
+            BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data() + (size_t)done * m, (size_t)S * m, cudaMemcpyHostToDevice, h->stream));
+        }
         if (tape) {
             BP_CUDA(h, cudaMemcpyAsync(d_tape, tape + (size_t)done * stride, sizeof(double) * (size_t)S * stride,
                                        cudaMemcpyHostToDevice, h->stream));
@@ -240,15 +263,15 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
             k4_fill_tape_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(d_tape, S, stride, seed, first_sample + done);
             BP_CHECK_LAUNCH(h);
         }
-        k4_init_kernel<<<(unsigned)((S + 127) / 128), 128, 0, h->stream>>>(d_s0, m, n, eta >= 0.0 ? d_w : nullptr, d_tape, stride, S,
+        k4_init_kernel<<<(unsigned)((S + 127) / 128), 128, 0, h->stream>>>(d_s0, s0_stride, m, n, eta >= 0.0 ? d_w : nullptr, d_tape, stride, S,
                                                                           d_occ_s, d_occ_t, d_rem, d_nrem, d_steps);
         BP_CHECK_LAUNCH(h);
         for (int k = 1; k <= n; ++k) {
             const int chunks = bp_k3_chunks(h, k, S), W = bp_k3_width(k);
-            if ((rc = bp_k3_launch(h, dU, m, d_occ_s, d_occ_t, d_steps, k, S, chunks, d_part, d_terms))) return rc;
+            if ((rc = bp_k3_launch(h, dU, u_stride, m, d_occ_s, d_occ_t, d_steps, k, S, chunks, d_part, d_terms))) return rc;
             K3Finish a;
             memset(&a, 0, sizeof(a));
-            a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = k - 1; a.partials = d_part;
+            a.U = dU; a.u_stride = u_stride; a.m = m; a.W = W; a.chunks = chunks; a.step = k - 1; a.partials = d_part;
             a.terms = d_terms; a.groups = bp_k3_groups(k);
             a.occ_s = d_occ_s; a.occ_t = d_occ_t;
             a.tape = d_tape; a.tape_stride = stride; a.remaining = d_rem; a.n_remaining = d_nrem; a.n = n;
@@ -262,6 +285,18 @@ int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int6
         BP_CUDA(h, cudaStreamSynchronize(h->stream));
     }
     return BP_OK;
+}
+
+int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int64_t n_samples, double eta, uint64_t seed,
+                     int64_t first_sample, const double *tape, int32_t *out) {
+    return gccb_simulate_impl(h, U, m, s, false, n_samples, eta, seed, first_sample, tape, 0, out, "bp_gccb_simulate");
+}
+
+int bp_gccb_simulate_batch(bp_handle h, const double *Us, int m, const int32_t *states, int64_t n_samples, uint64_t seed,
+                           int64_t first_sample, const double *tape, int tape_particles, int32_t *out) {
+    if (tape && tape_particles < 0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate_batch: tape_particles=%d", tape_particles);
+    return gccb_simulate_impl(h, Us, m, states, true, n_samples, -1.0, seed, first_sample, tape, tape ? tape_particles : 0, out,
+                              "bp_gccb_simulate_batch");
 }
 
 }  // extern "C"

@@ -3,8 +3,8 @@
 Mirrors ``StrategyType`` / ``SimulationStrategyFactory`` of the reference
 (theboss/simulation_strategies/simulation_strategy_factory.py:36-226) for the strategies on the permanent
 hot path.  The enum keeps every reference member (so values match), but only the GCC family is built
-here; the mean-field, R-backed and BOBS strategies are outside this package's scope (SURVEY.md section 8
-marks them out of scope / next) and raise ``NotImplementedError`` naming the reference class to use.
+here (GCC, lossy-network GCC-B, uniform-loss GCC and both BOBS variants); the mean-field and R-backed strategies
+are outside this package's scope (SURVEY.md section 8 marks them out of scope) and raise ``NotImplementedError`` naming the reference class to use.
 Like the reference the factory deep-copies the calculator it is given (:58, :107, :186).
 """
 import enum
@@ -17,6 +17,8 @@ from .generalized_cliffords_uniform_losses_simulation_strategy import (
 from .lossy_networks_generalized_cliffords_simulation_strategy import (
     LossyNetworksGeneralizedCliffordsSimulationStrategy,
 )
+from .lossy_state_approximated_simulation_strategy import LossyStateApproximationSimulationStrategy
+from .nonuniform_losses_approximation_strategy import NonuniformLossesApproximationStrategy
 from .simulation_strategy_interface import SimulationStrategyInterface
 
 
@@ -37,8 +39,6 @@ _OUT_OF_SCOPE = {
     StrategyType.UNIFORM_LOSS: "theboss.simulation_strategies.uniform_loss_simulation_strategy.UniformLossSimulationStrategy",
     StrategyType.CLIFFORD_R: "theboss.simulation_strategies.cliffords_r_simulation_strategy.CliffordsRSimulationStrategy",
     StrategyType.LOSSLESS_MODES_STRATEGY: "(no reference class is mapped to this member either)",
-    StrategyType.BOBS: "theboss.simulation_strategies.nonuniform_losses_approximation_strategy.NonuniformLossesApproximationStrategy",
-    StrategyType.UNIFORM_LOSSES_BOBS: "theboss.simulation_strategies.lossy_state_approximated_simulation_strategy.LossyStateApproximationSimulationStrategy",
 }
 
 
@@ -68,5 +68,10 @@ class SimulationStrategyFactory:
             # simulation_strategy_factory.py:175-181 of the reference: version A with per-particle Bernoulli losses
             return GeneralizedCliffordsUniformLossesSimulationStrategy(
                 calc, getattr(self.experiment_configuration, "uniform_transmissivity", 1.0))
+        cfg = self.experiment_configuration
+        if kind == StrategyType.BOBS:            # simulation_strategy_factory.py:183-192 of the reference
+            return NonuniformLossesApproximationStrategy(calc, cfg.number_of_modes - cfg.hierarchy_level)
+        if kind == StrategyType.UNIFORM_LOSSES_BOBS:   # :194-205
+            return LossyStateApproximationSimulationStrategy(calc, cfg.uniform_transmissivity, cfg.hierarchy_level)
         raise NotImplementedError(
             f"{kind.name} is outside the permanent hot path built here; use the reference class {_OUT_OF_SCOPE.get(kind)}")
