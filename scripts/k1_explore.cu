@@ -344,6 +344,70 @@ k1_e(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, doub
 }
 
 
+// variant E3: E with 32-bit loop bookkeeping
+template <int NCH, int UNR, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k1_e3(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, double *__restrict__ partials) {
+    __shared__ double2 sA2[N * N];
+    __shared__ double red[4 * (THREADS / 32)];
+    for (int e = threadIdx.x; e < N * N; e += THREADS) {
+        double2 v = reinterpret_cast<const double2 *>(A)[e];
+        sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
+    }
+    __syncthreads();
+    const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    const uint64_t start = lo + gtid * span;     // lo, span: multiples of 64
+    dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
+    if (start < hi) {
+        const uint64_t end = (hi - start < span) ? hi : start + span;   // multiple of UNR
+        double sr[N], si[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+        const uint64_t g0 = start ^ (start >> 1);
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            const double sg = ((g0 >> i) & 1ull) ? -0.5 : 0.5;
+            const double2 *row = sA2 + i * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+        }
+        cplx p = prod_rr<N, NCH>(sr, si);
+        double wr = p.re, wi = p.im;             // term `start` (even index: +)
+        // 32-bit bookkeeping: block counter counts down, the low word of the step index drives ctz / signs;
+        // the (rare) blocks whose low word is zero take the 64-bit path.
+        uint32_t nblk = (uint32_t)((end - start) / UNR);
+        uint32_t lo32 = (uint32_t)start;
+        uint32_t hi32 = (uint32_t)(start >> 32);
+#pragma unroll 1
+        for (;;) {
+            const double sg_half = ((lo32 >> cx_log2(UNR)) & 1u) ? 1.0 : -1.0;
+            EStep<NCH, UNR, 1>::run(sr, si, wr, wi, sg_half);
+            lo32 += UNR;
+            if (--nblk == 0) break;
+            if ((lo32 & 63u) == 0u) { acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi); wr = 0.0; wi = 0.0; }
+            int r; double sg;
+            if (lo32 & 0x7fffffffu) {
+                r = __ffs((int)lo32) - 1;                       // <= 30, so bit r + 1 is in the low word
+                sg = ((lo32 >> (r + 1)) & 1u) ? 1.0 : -1.0;
+            } else {
+                if (lo32 == 0u) ++hi32;
+                const uint64_t I0 = ((uint64_t)hi32 << 32) | lo32;
+                r = ctz64(I0);
+                sg = ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0;
+            }
+            const double2 *row = sA2 + r * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+            p = prod_rr<N, NCH>(sr, si);
+            wr += p.re; wi += p.im;
+        }
+        acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+    }
+    block_reduce_dd(acc_re, acc_im, red);
+    if (threadIdx.x == 0) { double *o = partials + 4 * (size_t)blockIdx.x; o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo; }
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // variant F: fully warp-uniform inner structure.  Every thread owns `nwin` whole 64-step windows;
 // inside a window the loop counters are block-uniform, so every flipped row (0..5) is addressed
@@ -907,6 +971,8 @@ int main(int argc, char **argv) {
         {"E2 nch4 u4 256x1", k1_e2<4, 4, 256, 1>, 256, 1, 1}, {"E2 nch4 u8 256x1", k1_e2<4, 8, 256, 1>, 256, 1, 1},
         {"E2 nch3 u4 256x1", k1_e2<3, 4, 256, 1>, 256, 1, 1}, {"E2 nch4 u4 384x1", k1_e2<4, 4, 384, 1>, 384, 1, 1},
         {"E2 nch4 u2 256x1", k1_e2<4, 2, 256, 1>, 256, 1, 1}, {"E2 nch4 u2 384x1", k1_e2<4, 2, 384, 1>, 384, 1, 1},
+        {"E3 nch2 u4 256x1", k1_e3<2, 4, 256, 1>, 256, 1, 1}, {"E3 nch4 u4 256x1", k1_e3<4, 4, 256, 1>, 256, 1, 1},
+        {"E3 nch2 u8 256x1", k1_e3<2, 8, 256, 1>, 256, 1, 1}, {"E3 nch3 u4 256x1", k1_e3<3, 4, 256, 1>, 256, 1, 1},
         {"G u4 256x1", k1_g<4, 256, 1>, 256, 1, 1},  {"G u8 256x1", k1_g<8, 256, 1>, 256, 1, 1},  {"G u16 256x1", k1_g<16, 256, 1>, 256, 1, 1},
         {"G u2 256x1", k1_g<2, 256, 1>, 256, 1, 1},  {"G u4 384x1", k1_g<4, 384, 1>, 384, 1, 1},  {"G u8 384x1", k1_g<8, 384, 1>, 384, 1, 1},
         {"G u8 128x2", k1_g<8, 128, 2>, 128, 2, 1},  {"G u8 128x3", k1_g<8, 128, 3>, 128, 3, 1},  {"G u4 128x3", k1_g<4, 128, 3>, 128, 3, 1},
@@ -1004,6 +1070,7 @@ int main(int argc, char **argv) {
             {"H u16 c2 384", k1_h<16, 384, 2>, 384},  {"H u32 c2 384", k1_h<32, 384, 2>, 384}, {"H u64 c1 384", k1_h<64, 384, 1>, 384},
             {"H u16 c1 256", k1_h<16, 256, 1>, 256},  {"H u32 c1 256", k1_h<32, 256, 1>, 256}, {"H u32 c2 256", k1_h<32, 256, 2>, 256},
             {"H u16 c1 448", k1_h<16, 448, 1>, 448},  {"H u32 c1 320", k1_h<32, 320, 1>, 320}, {"H u16 c3 384", k1_h<16, 384, 3>, 384},
+            {"H u32 c3 256", k1_h<32, 256, 3>, 256},  {"H u32 c4 256", k1_h<32, 256, 4>, 256}, {"H u32 c5 256", k1_h<32, 256, 5>, 256},
             {"H u64 c1 256", k1_h<64, 256, 1>, 256},  {"H u16 c1 128", k1_h<16, 128, 1>, 128}, {"H u32 c1 192", k1_h<32, 192, 1>, 192},
         };
         const uint64_t total_h = 1ull << (N - 1);
