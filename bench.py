@@ -208,7 +208,8 @@ def secondary_metrics(device):
         sub = min(10_000, 4 * cores)
         tc = cpu_parallel(lambda b: orc.guan_permanent(U, S[b], T[b], orc.CHIN_HUH, "d"), range(sub))
         out["c2_batched_n20_m40"] = {"items": 10_000, "seconds": t, "permanents_per_s": 10_000 / t,
-                                     "approx_useful_tflops": terms * (6 * 20 + 6 * 19 + 4) / t / 1e12,
+                                     # T * (2 d + 6 (n - 1) + 4) flops per item, d <= n distinct product-side modes
+                                     "useful_tflops_upper": terms * (2 * 20 + 6 * 19 + 4) / t / 1e12,
                                      "cpu_port": {"permanents_per_s": sub / tc, "cores": cores,
                                                   "sample": f"first {sub} items, oracle Chin-Huh double (reference algorithm: walks the input side, no symmetry halving)"}}
     except Exception as e:   # noqa: BLE001
@@ -254,6 +255,20 @@ def secondary_metrics(device):
         out["c5_uniform_losses_n30_m60"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t}
     except Exception as e:   # noqa: BLE001
         out["c5_uniform_losses_n30_m60"] = {"error": repr(e)}
+    try:   # C5 (ii): non-uniform losses through the 2m-mode dilation, n=30, m=60 (bounded sample count: every sample
+           # costs up to 3.4e11 flops)
+        from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import prepare_interferometer_matrix_in_expanded_space
+        U, U_lossy, s = workloads.c5_lossy(30, 60)
+        big = np.ascontiguousarray(prepare_interferometer_matrix_in_expanded_space(U_lossy))
+        s_big = np.concatenate([s, np.zeros(60, dtype=np.int32)])
+        S_n = 64
+        t0 = time.perf_counter()
+        res = h.gccb_simulate(big, s_big, S_n, seed=5)
+        t = time.perf_counter() - t0
+        out["c5_nonuniform_losses_n30_m60"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t,
+                                               "mean_particles_detected": float(res[:, :60].sum(axis=1).mean())}
+    except Exception as e:   # noqa: BLE001
+        out["c5_nonuniform_losses_n30_m60"] = {"error": repr(e)}
     try:   # C1: GCC (version A), n=5, m=10, 1000 samples through the strategy class
         from theboss_b200.boson_sampling_utilities.permanent_calculators.glynn_gray_permanent_calculator import GlynnGrayPermanentCalculator
         from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy

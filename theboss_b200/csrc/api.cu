@@ -14,9 +14,6 @@ int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int
 int bp_fp64_peak_launch(bp_context *h, int iters, double *d_sink);
 int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
                  long long B, double *d_out);
-#define BP_HAVE_K2 1
-#define BP_HAVE_K3 1
-#define BP_HAVE_K4 1
 
 static char g_global_err[512] = "no error";
 
@@ -317,28 +314,3 @@ int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const
 }
 
 }  // extern "C"
-
-// ---- entry points whose kernels have not landed yet (replaced one by one) ----------------------
-extern "C" {
-#ifndef BP_HAVE_K2
-int bp_perm_batched(bp_handle h, const double *, int, const uint8_t *, const uint8_t *, int64_t, int, double *) {
-    return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: not built into this library");
-}
-int bp_perm_batched_dev(bp_handle h, const double *, int, const uint8_t *, const uint8_t *, int64_t, int, double *) {
-    return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched_dev: not built into this library");
-}
-#endif
-#ifndef BP_HAVE_K3
-int bp_minors(bp_handle h, const double *, int, const int32_t *, const int32_t *, int, double *) {
-    return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_minors: not built into this library");
-}
-int bp_gccb_pmf(bp_handle h, const double *, int, const int32_t *, const int32_t *, double *, double *) {
-    return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_gccb_pmf: not built into this library");
-}
-#endif
-#ifndef BP_HAVE_K4
-int bp_gccb_simulate(bp_handle h, const double *, int, const int32_t *, int64_t, double, uint64_t, int64_t, const double *, int32_t *) {
-    return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_gccb_simulate: not built into this library");
-}
-#endif
-}
