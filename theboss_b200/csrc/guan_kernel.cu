@@ -74,14 +74,18 @@ __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, 
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+#define K2_PMAX 512
+#define K2_REGROW_MAX_N 22   // up to this N the row of the inner digit is kept in registers (4N extra registers)
+
 template <int N>
 struct K2Cfg {
-    static constexpr int MINB = (N <= 4) ? 6 : (N <= 16) ? 4 : (N <= 26) ? 3 : 2;
+    static constexpr bool REGROW = (N <= K2_REGROW_MAX_N);
+    static constexpr int MINB = (N <= 8) ? 4 : (N <= 12) ? 3 : (N <= K2_REGROW_MAX_N) ? 2 : (N <= 26) ? 3 : 2;
 };
 
 template <int N>
 __device__ __forceinline__ void k2_product(const double (&sr)[N], const double (&si)[N], double &pr, double &pi) {
-    constexpr int NCH = (N >= 9) ? 3 : (N >= 4 ? 2 : 1);
+    constexpr int NCH = (N > K2_REGROW_MAX_N) ? 4 : (N >= 4 ? 2 : 1);   // fewer chains where the inner row occupies registers
     cplx p[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { p[c].re = sr[c]; p[c].im = si[c]; }
@@ -90,32 +94,52 @@ __device__ __forceinline__ void k2_product(const double (&sr)[N], const double (
         cplx s = {sr[j], si[j]};
         p[j % NCH] = cmul(p[j % NCH], s);
     }
-    cplx r = p[0];
 #pragma unroll
-    for (int c = 1; c < NCH; ++c) r = cmul(r, p[c]);
-    pr = r.re; pi = r.im;
+    for (int stride = 1; stride < NCH; stride <<= 1)
+#pragma unroll
+        for (int c = 0; c + stride < NCH; c += 2 * stride) p[c] = cmul(p[c], p[c + stride]);
+    pr = p[0].re; pi = p[0].im;
 }
 
+// shared-memory load the compiler may not hoist out of the term loop (keeps the inner row out of registers for large N)
+__device__ __forceinline__ double2 k2_lds_nohoist(const double2 *p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+// The walk of one item is organised like the minors kernel's (minors_kernel.cu): rows of L0 + 1 terms that
+// differ only in the inner digit 0 (largest multiplicity; swept up on even rows, down on odd ones), rows
+// indexed by the sub-walk over digits 1 .. D-1; the low digits of that sub-walk follow a per-block table
+// (period P), the generic Guan stepper only carries into the digits above it.  Threads own whole periods.
 template <int N>
 __global__ void __launch_bounds__(GW_THREADS, K2Cfg<N>::MINB)
 k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ S,
                const unsigned char *__restrict__ T, const K2Meta *__restrict__ meta,
                const int *__restrict__ order, int first, double *__restrict__ partials) {
+    constexpr bool REGROW = K2Cfg<N>::REGROW;
     __shared__ GuanItem item;
     __shared__ short col_mode[N];
     __shared__ double2 X2[N * N];                       // 2 * X[v][j], D <= N rows
     __shared__ unsigned char rdig[N * GW_THREADS];      // per-thread digit vectors (column = thread)
     __shared__ double red[4 * (GW_THREADS / 32)];
+    __shared__ double bin0[BP_MAX_N + 2];
+    __shared__ double blow[K2_PMAX];
+    __shared__ unsigned short steptab[K2_PMAX];
+    __shared__ int low_digits;
+    __shared__ unsigned period;
 
     const int b = order[first + blockIdx.x];
     const K2Meta me = meta[b];   // (blockIdx.y = chunk of this item's walk)
     const unsigned char *walk = (me.walk_outputs ? T : S) + (long long)b * m;
     const unsigned char *prod = (me.walk_outputs ? S : T) + (long long)b * m;
     if (threadIdx.x == 0) {
-        guan_item_build(item, walk, m);
+        guan_item_build(item, walk, m, /*inner_first=*/true);
         int c = 0;
         for (int v = 0; v < m; ++v)
             for (int a = 0; a < prod[v] && c < N; ++a) col_mode[c++] = (short)v;
+        for (int r = 0; r <= (int)item.lim[0]; ++r)
+            bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
     }
     __syncthreads();
     const int D = item.D;
@@ -127,50 +151,146 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
         const double2 u = me.walk_outputs ? U2[wm * m + pm] : U2[pm * m + wm];
         X2[e] = make_double2(2.0 * u.x, 2.0 * u.y);
     }
+    const int L0 = item.lim[0];
+    const unsigned long long rows = item.terms / (unsigned long long)(L0 + 1);
+    const unsigned long long nthreads = (unsigned long long)gridDim.y * GW_THREADS;
+    if (threadIdx.x == 0) {
+        unsigned long long raw = (rows + nthreads - 1) / nthreads, P = 1;
+        int a = 0;
+        for (int v = 1; v < D; ++v) {
+            const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
+            if (nxt * 16 > raw || nxt > K2_PMAX) break;
+            P = nxt; a = v;
+        }
+        period = (unsigned)P;
+        low_digits = a;
+    }
+    __syncthreads();
+    const unsigned P = period;
+    const int a_low = low_digits;
+    for (unsigned p = threadIdx.x; p < P; p += GW_THREADS) {
+        double bprod = 1.0;
+        unsigned q = p, qm = p ? p - 1 : 0;
+        int chg = 0, up = 0;
+        for (int v = 1; v <= a_low; ++v) {
+            const unsigned R = (unsigned)item.lim[v] + 1u;
+            unsigned d = q % R; q /= R;
+            unsigned dm = qm % R; qm /= R;
+            const int rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
+            const int rm = (qm & 1u) ? (int)item.lim[v] - (int)dm : (int)dm;
+            if (p && rv != rm) { chg = v; up = rv > rm; }
+            double c = gw_binom(item.mult[v], rv);
+            if (v == D - 1) c *= gw_top_weight(item, rv);
+            bprod *= c;
+        }
+        blow[p] = bprod;
+        steptab[p] = (unsigned short)(chg | (up << 8));
+    }
     __syncthreads();
 
-    // grid = (items, chunks): the walk of one item is cut into gridDim.y * GW_THREADS contiguous spans
-    const unsigned long long total = item.terms;
-    const unsigned long long nspans = (unsigned long long)gridDim.y * GW_THREADS;
-    unsigned long long span = (total + nspans - 1) / nspans;
-    if (span < 1) span = 1;
-    const unsigned long long start = ((unsigned long long)blockIdx.y * GW_THREADS + threadIdx.x) * span;
+    // whole periods are dealt out to the threads of all chunk blocks of this item
+    const unsigned long long nper = rows / P;
+    const unsigned long long tidx = (unsigned long long)blockIdx.y * GW_THREADS + threadIdx.x;
+    const unsigned long long pbase = nper / nthreads, prem = nper % nthreads;
+    const unsigned long long my_periods = pbase + (tidx < prem ? 1ull : 0ull);
+    const unsigned long long row_start = (tidx * pbase + (tidx < prem ? tidx : prem)) * P;
     dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
 
-    if (start < total) {
-        const unsigned long long end = (total - start < span) ? total : start + span;
+    if (my_periods > 0) {
+        const unsigned long long row_end = row_start + my_periods * P;
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
-        guan_seek(item, start, r, st);
+        const unsigned long long hi0 = row_start / P;
+        guan_seek(item, hi0, r, st, /*v0=*/a_low + 1);
+        int pos = (hi0 & 1ull) ? (int)P - 1 : 0;
+        int pdir = (hi0 & 1ull) ? -1 : 1;
+        unsigned off = 0;
+        int r0 = (row_start & 1ull) ? L0 : 0;
+        int dir0 = (row_start & 1ull) ? -1 : 1;
         double sr[N], si[N];
+        double x0r[REGROW ? N : 1], x0i[REGROW ? N : 1];
 #pragma unroll
         for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+        int par = r0;
+        {
+            unsigned q = (unsigned)pos;
 #pragma unroll 1
-        for (int v = 0; v < D; ++v) {
-            const double c = 0.5 * (double)((int)item.mult[v] - 2 * (int)r[v * GW_THREADS]);
-            const double2 *row = X2 + v * N;
+            for (int v = 0; v < D; ++v) {
+                int rv;
+                if (v == 0) rv = r0;
+                else if (v <= a_low) {
+                    const unsigned R = (unsigned)item.lim[v] + 1u;
+                    const unsigned d = q % R; q /= R;
+                    rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
+                } else rv = (int)r[v * GW_THREADS];
+                if (v > 0) par += rv;
+                const double c = 0.5 * (double)((int)item.mult[v] - 2 * rv);
+                const double2 *row = X2 + v * N;
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 a = row[j];
-                sr[j] = fma(c, a.x, sr[j]);
-                si[j] = fma(c, a.y, si[j]);
+                for (int j = 0; j < N; ++j) {
+                    const double2 a = row[j];
+                    sr[j] = fma(c, a.x, sr[j]);
+                    si[j] = fma(c, a.y, si[j]);
+                }
             }
         }
-        double pr, pi;
-        k2_product<N>(sr, si, pr, pi);
-        double w = (start & 1ull) ? -st.binom : st.binom;
-        double wr = w * pr, wi = w * pi;
+        if (REGROW) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = X2[j]; x0r[j] = a.x; x0i[j] = a.y; }
+        }
+        double sgn = (par & 1) ? -1.0 : 1.0;
+        double bout = st.binom * blow[pos];
+        double wr = 0.0, wi = 0.0;
         unsigned cnt = 0;
+
 #pragma unroll 1
-        for (unsigned long long I = start + 1; I < end; ++I) {
-            if (++cnt == 64u) {
-                cnt = 0;
-                acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
-                wr = 0.0; wi = 0.0;
+        for (unsigned long long q = row_start;;) {
+            // ---- inner sweep over digit 0
+#pragma unroll 1
+            for (int step = 0;; ++step) {
+                double pr, pi;
+                k2_product<N>(sr, si, pr, pi);
+                const double w = sgn * bout * bin0[r0];
+                wr = fma(w, pr, wr);
+                wi = fma(w, pi, wi);
+                if (++cnt == 64u) {
+                    cnt = 0;
+                    acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+                    wr = 0.0; wi = 0.0;
+                }
+                if (step == L0) break;
+                r0 += dir0;
+                sgn = -sgn;
+                const double sg = (dir0 > 0) ? -1.0 : 1.0;        // sums -= 2 * dir0 * X[0]
+                if (REGROW) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { sr[j] = fma(sg, x0r[j], sr[j]); si[j] = fma(sg, x0i[j], si[j]); }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { const double2 a = k2_lds_nohoist(X2 + j); sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+                }
             }
-            int delta;
-            const int v = guan_step(item, r, st, delta);
-            const double sg = (delta > 0) ? -1.0 : 1.0;       // sums -= 2 * delta * X[v]
+            dir0 = -dir0;
+            // ---- next row
+            if (++q >= row_end) break;
+            int v, up;
+            if (++off < P) {
+                const int idx = (pdir > 0) ? pos + 1 : pos;
+                const unsigned e = steptab[idx];
+                v = (int)(e & 0xffu);
+                up = (pdir > 0) ? (int)(e >> 8) : 1 - (int)(e >> 8);
+                pos += pdir;
+                bout = st.binom * blow[pos];
+            } else {
+                int delta;
+                v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+                up = delta > 0;
+                off = 0;
+                pdir = -pdir;
+                bout = st.binom * blow[pos];
+            }
+            sgn = -sgn;
+            const double sg = up ? -1.0 : 1.0;
             const double2 *row = X2 + v * N;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
@@ -178,10 +298,6 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
                 sr[j] = fma(sg, a.x, sr[j]);
                 si[j] = fma(sg, a.y, si[j]);
             }
-            k2_product<N>(sr, si, pr, pi);
-            w = (I & 1ull) ? -st.binom : st.binom;
-            wr = fma(w, pr, wr);
-            wi = fma(w, pi, wi);
         }
         acc_re = dd_add_d(acc_re, wr);
         acc_im = dd_add_d(acc_im, wi);
@@ -268,7 +384,7 @@ int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS
         }
         // chunks per item: enough blocks to fill the GPU a few times over, but at least ~256 terms per thread
         long long by_fill = ((long long)h->sm_count * 12 + count - 1) / count;
-        long long by_work = (long long)(ldexp(1.0, n - 1) / (GW_THREADS * 256.0));
+        long long by_work = (long long)(ldexp(1.0, n - 1) / (GW_THREADS * 512.0));
         long long chunks = by_fill < by_work ? by_fill : by_work;
         if (chunks < 1) chunks = 1;
         if (chunks > 4096) chunks = 4096;
