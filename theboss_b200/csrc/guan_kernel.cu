@@ -75,12 +75,14 @@ __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, 
 // main kernel
 // ---------------------------------------------------------------------------------------------
 #define K2_PMAX 512
-#define K2_REGROW_MAX_N 22   // up to this N the row of the inner digit is kept in registers (4N extra registers)
+#ifndef K2_REGROW_MAX_N
+#define K2_REGROW_MAX_N 12   // up to this N the row of the inner digit is kept in registers (4N extra registers); measured at N=20: 3 warps/SMSP with LDS rows beat 2 warps with register rows (11.8 vs 12.3 ms on config 2)
+#endif
 
 template <int N>
 struct K2Cfg {
     static constexpr bool REGROW = (N <= K2_REGROW_MAX_N);
-    static constexpr int MINB = (N <= 8) ? 4 : (N <= 12) ? 3 : (N <= K2_REGROW_MAX_N) ? 2 : (N <= 26) ? 3 : 2;
+    static constexpr int MINB = (N <= 8) ? 4 : (N <= 26) ? 3 : 2;
 };
 
 template <int N>
