@@ -129,3 +129,36 @@ def test_batched_shape_error(handle):
     T = np.array([[0, 1, 1, 0], [1, 1, 0, 0]], dtype=np.uint8)
     with pytest.raises(AttributeError):
         handle.perm_batched(U, S, T)
+
+
+def test_device_pointer_entry_points_match_host_entry_points(orc):
+    """`_dev` variants (inputs resident in HBM, caller-owned stream) against the host-pointer calls."""
+    import torch
+    from theboss_b200 import _native
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream(0)
+    h = _native.Handle(0, stream_ptr=stream.cuda_stream)
+    rng = np.random.RandomState(4)
+    m, n, B = 10, 7, 40
+    U = workloads.haar(m, 3)
+    S = np.array([_occ(rng, m, n) for _ in range(B)])
+    T = np.array([_occ(rng, m, n) for _ in range(B)])
+    dU = torch.from_numpy(U.view(np.float64).copy()).to(dev)
+    dS, dT = torch.from_numpy(S).to(dev), torch.from_numpy(T).to(dev)
+    d_out = torch.zeros(2 * B, dtype=torch.float64, device=dev)
+    h.perm_batched_dev(dU.data_ptr(), m, dS.data_ptr(), dT.data_ptr(), B, _native.FORMULA_GLYNN, d_out.data_ptr())
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.complex128)
+    want = _native.default_handle(0).perm_batched(U, S, T)
+    assert np.array_equal(got, want)
+    # K1 range on device pointers
+    A = workloads.c4_matrix(14)
+    dA = torch.from_numpy(A.view(np.float64).copy()).to(dev)
+    d_part = torch.zeros(4, dtype=torch.float64, device=dev)
+    h.glynn_matrix_range_dev(dA.data_ptr(), 14, 0, 1 << 13, d_part.data_ptr())
+    torch.cuda.synchronize()
+    p = d_part.cpu().numpy()
+    got1 = complex(p[0] + p[1], p[2] + p[3]) / (1 << 13)
+    want1 = orc.glynn_matrix(A, "ld")
+    assert abs(got1 - want1) <= 1e-12 * abs(want1)
+    h.close()
