@@ -480,6 +480,74 @@ k1_e4(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, dou
     if (threadIdx.x == 0) { double *o = partials + 4 * (size_t)blockIdx.x; o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo; }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// variant E5: E (UNR = 4) with the loop nest of E4 -- outer loop over 64-step windows (64-bit, per thread),
+// inner loop over the 16 blocks of a window with a small uniform counter that yields the block-closing row
+// (2 + ctz(q)) and its sign without 64-bit arithmetic; the row itself still comes from shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int NCH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k1_e5(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, double *__restrict__ partials) {
+    __shared__ double2 sA2[N * N];
+    __shared__ double red[4 * (THREADS / 32)];
+    for (int e = threadIdx.x; e < N * N; e += THREADS) {
+        double2 v = reinterpret_cast<const double2 *>(A)[e];
+        sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
+    }
+    __syncthreads();
+    const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    const uint64_t start = lo + gtid * span;     // lo, span, hi: multiples of 64
+    dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
+    if (start < hi) {
+        const uint64_t end = (hi - start < span) ? hi : start + span;
+        double sr[N], si[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+        const uint64_t g0 = start ^ (start >> 1);
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            const double sg = ((g0 >> i) & 1ull) ? -0.5 : 0.5;
+            const double2 *row = sA2 + i * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+        }
+        double wr = 0.0, wi = 0.0;
+        const uint32_t nwin = (uint32_t)((end - start) >> 6);
+        uint64_t Iw = start;
+#pragma unroll 1
+        for (uint32_t w = 0; w < nwin; ++w, Iw += 64) {
+            int r = 0;
+            double sg = 0.0;
+            if (w > 0) {
+                acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi); wr = 0.0; wi = 0.0;
+                r = ctz64(Iw);
+                sg = ((Iw >> (r + 1)) & 1ull) ? 1.0 : -1.0;
+            }
+            const double sg_top = ((Iw >> 6) & 1ull) ? 1.0 : -1.0;
+#pragma unroll 1
+            for (uint32_t q = 0; q < 16; ++q) {
+                // block-closing flip of the previous block: q = 0 -> window boundary (r, sg above; nothing for the very first block)
+                if (q > 0) {
+                    const int c = __ffs((int)q) - 1;                         // 0..3 -> rows 2..5
+                    r = 2 + c;
+                    sg = (c == 3) ? sg_top : (((q >> (c + 1)) & 1u) ? 1.0 : -1.0);
+                }
+                const double2 *row = sA2 + r * N;
+#pragma unroll
+                for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+                cplx p = prod_rr<N, NCH>(sr, si);
+                wr += p.re; wi += p.im;
+                const double sg_half = (q & 1u) ? 1.0 : -1.0;                // bit 2 of the step offset
+                EStep<NCH, 4, 1>::run(sr, si, wr, wi, sg_half);
+            }
+        }
+        acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+    }
+    block_reduce_dd(acc_re, acc_im, red);
+    if (threadIdx.x == 0) { double *o = partials + 4 * (size_t)blockIdx.x; o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // variant F: fully warp-uniform inner structure.  Every thread owns `nwin` whole 64-step windows;
 // inside a window the loop counters are block-uniform, so every flipped row (0..5) is addressed
@@ -1047,6 +1115,8 @@ int main(int argc, char **argv) {
         {"E3 nch2 u8 256x1", k1_e3<2, 8, 256, 1>, 256, 1, 1}, {"E3 nch3 u4 256x1", k1_e3<3, 4, 256, 1>, 256, 1, 1},
         {"E4 nch2 256x1", k1_e4<2, 256, 1>, 256, 1, 1}, {"E4 nch4 256x1", k1_e4<4, 256, 1>, 256, 1, 1},
         {"E4 nch3 256x1", k1_e4<3, 256, 1>, 256, 1, 1}, {"E4 nch2 384x1", k1_e4<2, 384, 1>, 384, 1, 1},
+        {"E5 nch2 256x1", k1_e5<2, 256, 1>, 256, 1, 1}, {"E5 nch4 256x1", k1_e5<4, 256, 1>, 256, 1, 1},
+        {"E5 nch3 256x1", k1_e5<3, 256, 1>, 256, 1, 1},
         {"G u4 256x1", k1_g<4, 256, 1>, 256, 1, 1},  {"G u8 256x1", k1_g<8, 256, 1>, 256, 1, 1},  {"G u16 256x1", k1_g<16, 256, 1>, 256, 1, 1},
         {"G u2 256x1", k1_g<2, 256, 1>, 256, 1, 1},  {"G u4 384x1", k1_g<4, 384, 1>, 384, 1, 1},  {"G u8 384x1", k1_g<8, 384, 1>, 384, 1, 1},
         {"G u8 128x2", k1_g<8, 128, 2>, 128, 2, 1},  {"G u8 128x3", k1_g<8, 128, 3>, 128, 3, 1},  {"G u4 128x3", k1_g<4, 128, 3>, 128, 3, 1},

@@ -143,16 +143,17 @@ glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64
 
 __constant__ double2 c_A2[BP_MAX_N * BP_MAX_N];   // 2*A of the permanent in flight (row stride N)
 
-template <int N>
-__device__ __forceinline__ void k1b_product(const double (&sr)[N], const double (&si)[N], double &pr, double &pi) {
+// product of the N column sums in two chains; the final chain-times-chain multiplication is fused into the
+// window accumulator (PLUS: w += p, else w -= p)
+template <int N, bool PLUS>
+__device__ __forceinline__ void k1b_product_acc(const double (&sr)[N], const double (&si)[N], double &wr, double &wi) {
     cplx p0 = {sr[0], si[0]}, p1 = {sr[1], si[1]};   // two chains measured best under the 255-register cap
 #pragma unroll
     for (int j = 2; j < N; ++j) {
         cplx s = {sr[j], si[j]};
         if (j & 1) p1 = cmul(p1, s); else p0 = cmul(p0, s);
     }
-    p0 = cmul(p0, p1);
-    pr = p0.re; pi = p0.im;
+    if (PLUS) cmul_acc(wr, wi, p0, p1); else cmul_sub(wr, wi, p0, p1);
 }
 
 template <int N, int ROW, int MODE>   // MODE 0: subtract, 1: add, 2: run-time sign
@@ -198,21 +199,17 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
                 si[j] = fma(sg, a.y, si[j]);
             }
         }
-        double pr, pi;
-        k1b_product<N>(sr, si, pr, pi);
-        double wr = pr, wi = pi;                       // step `start` (even: +)
+        double wr = 0.0, wi = 0.0;
+        k1b_product_acc<N, true>(sr, si, wr, wi);      // step `start` (even: +)
 #pragma unroll 1
         for (uint64_t I0 = start;;) {
             // steps I0+1, I0+2, I0+3 with I0 = 0 (mod 4): rows 0, 1, 0; new delta = -1, (bit 2 of I0 ? +1 : -1), +1
             k1b_flip_const<N, 0, 0>(sr, si, 0.0);
-            k1b_product<N>(sr, si, pr, pi);
-            wr -= pr; wi -= pi;
+            k1b_product_acc<N, false>(sr, si, wr, wi);
             k1b_flip_const<N, 1, 2>(sr, si, ((I0 >> 2) & 1ull) ? 1.0 : -1.0);
-            k1b_product<N>(sr, si, pr, pi);
-            wr += pr; wi += pi;
+            k1b_product_acc<N, true>(sr, si, wr, wi);
             k1b_flip_const<N, 0, 1>(sr, si, 0.0);
-            k1b_product<N>(sr, si, pr, pi);
-            wr -= pr; wi -= pi;
+            k1b_product_acc<N, false>(sr, si, wr, wi);
             I0 += 4;
             if (I0 >= end) break;
             if (((uint32_t)I0 & 63u) == 0u) {
@@ -230,8 +227,7 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
                 sr[j] = fma(sg, a.x, sr[j]);
                 si[j] = fma(sg, a.y, si[j]);
             }
-            k1b_product<N>(sr, si, pr, pi);
-            wr += pr; wi += pi;
+            k1b_product_acc<N, true>(sr, si, wr, wi);
         }
         acc_re = dd_add_d(acc_re, wr);
         acc_im = dd_add_d(acc_im, wi);

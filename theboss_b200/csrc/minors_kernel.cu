@@ -251,10 +251,12 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
                 // suffix pass: leave-one-out products, accumulate
 #pragma unroll
                 for (int j = C - 1; j >= 0; --j) {
-                    cplx L = (j == 0) ? suf : cmul(pre[j], suf);
-                    ar[j] += L.re;
-                    ai[j] += L.im;
-                    if (j > 0) { cplx cj = {cr[j], ci[j]}; suf = cmul(suf, cj); }
+                    if (j == 0) { ar[0] += suf.re; ai[0] += suf.im; }
+                    else {
+                        cmul_acc(ar[j], ai[j], pre[j], suf);          // acc_j += prefix_j * suffix_j, fused
+                        cplx cj = {cr[j], ci[j]};
+                        suf = cmul(suf, cj);
+                    }
                 }
                 if (step == L0) break;
                 // next value of digit 0: c -= 2 * dir0 * X[0]
