@@ -29,6 +29,11 @@ import sys
 import threading
 import time
 
+# keep stdout to the one JSON line: NCCL prints a version banner there at NCCL_DEBUG=VERSION, and it reads the
+# variable when torch first touches it, so this has to happen before torch is imported
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -324,9 +329,6 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
