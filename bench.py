@@ -29,10 +29,10 @@ import sys
 import threading
 import time
 
-# keep stdout to the one JSON line: NCCL prints a version banner there at NCCL_DEBUG=VERSION, and it reads the
-# variable when torch first touches it, so this has to happen before torch is imported
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# keep stdout to the one JSON line: NCCL prints a version banner there at NCCL_DEBUG=VERSION (and WARN); the
+# variable is read when NCCL initialises, so drop it before torch is imported (INFO etc. are left alone)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]
 
 import numpy as np
 

@@ -10,8 +10,8 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"     # before torch is imported: keeps NCCL's banner off stdout
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]     # before torch is imported: keeps NCCL's banner off stdout
 import numpy as np
 import torch
 import torch.distributed as dist
