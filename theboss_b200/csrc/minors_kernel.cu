@@ -433,19 +433,21 @@ static void k3_reg_all(int lg) {
     k3_reg<LPG, 9>(lg); k3_reg<LPG, 10>(lg); k3_reg<LPG, 11>(lg); k3_reg<LPG, 12>(lg);
 }
 
-// Variant for k input columns: smallest padded width LPG * C >= k with C <= max_c, preferring fewer
-// lanes per group.  max_c defaults to K3_DEFAULT_MAX_C; BP_K3_MAX_C overrides it (tuning).
+// Variant for k input columns: smallest padded width LPG * C >= k with C <= max_c, preferring fewer lanes per
+// group.  max_c is 8, except k = 21 .. 24 where two lanes with up to 12 columns measured 4 % faster than four
+// lanes with 6 (no butterfly multiplies; 2 warps/SMSP).  BP_K3_MAX_C overrides the limit for all k (tuning).
 #define K3_DEFAULT_MAX_C 8
 static K3Variant k3_pick(int k) {
-    static int max_c = 0;
+    static int forced_max_c = 0;
     if (!g_k3_init) {
         k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3);
         const char *e = getenv("BP_K3_MAX_C");
-        max_c = e ? atoi(e) : K3_DEFAULT_MAX_C;
-        if (max_c < 7) max_c = 7;
-        if (max_c > K3_MAX_C) max_c = K3_MAX_C;
+        forced_max_c = e ? atoi(e) : 0;
+        if (forced_max_c > K3_MAX_C) forced_max_c = K3_MAX_C;
         g_k3_init = true;
     }
+    int max_c = (k >= 21 && k <= 24) ? K3_MAX_C : K3_DEFAULT_MAX_C;
+    if (forced_max_c >= 7) max_c = forced_max_c;
     int best_lg = -1, best_c = 0, best_w = 1 << 30;
     for (int lg = 0; lg < 4; ++lg) {
         const int lpg = 1 << lg;
