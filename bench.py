@@ -46,7 +46,7 @@ N_PHOTONS = 30
 METRIC = "glynn_permanents_per_s_n30"
 UNIT = "permanents/s"
 ALG_FLOPS = (8 * N_PHOTONS - 4) * 2.0 ** (N_PHOTONS - 1)
-ISSUE_SLOTS = (6 * N_PHOTONS - 2) * 2.0 ** (N_PHOTONS - 1)    # FP64 instructions per permanent
+ISSUE_SLOTS = (6 * N_PHOTONS - 4) * 2.0 ** (N_PHOTONS - 1)    # FP64 instructions per permanent (last multiply fused into the accumulation)
 NOMINAL_FP64_TFLOPS = 37.0
 
 

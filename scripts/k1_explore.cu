@@ -548,6 +548,147 @@ k1_e5(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, dou
     if (threadIdx.x == 0) { double *o = partials + 4 * (size_t)blockIdx.x; o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo; }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// variant E6: E (UNR = 4) tuned for 3 warps/SMSP (384 threads, 168 registers): ONE product chain whose last
+// multiplication is fused into the window accumulator; SMEMACC keeps the per-thread double-double
+// accumulators in shared memory (touched once per 64 steps) to free 8 registers.
+// ---------------------------------------------------------------------------------------------
+template <bool PLUS>
+__device__ __forceinline__ void e6_prod_acc(const double (&sr)[N], const double (&si)[N], double &wr, double &wi) {
+    cplx p = {sr[0], si[0]};
+#pragma unroll
+    for (int j = 1; j < N - 1; ++j) { cplx s = {sr[j], si[j]}; p = cmul(p, s); }
+    cplx last = {sr[N - 1], si[N - 1]};
+    if (PLUS) cmul_acc(wr, wi, p, last); else cmul_sub(wr, wi, p, last);
+}
+
+template <int THREADS, bool SMEMACC>
+__global__ void __launch_bounds__(THREADS, 1)
+k1_e6(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, double *__restrict__ partials) {
+    __shared__ double2 sA2[N * N];
+    __shared__ double red[4 * (THREADS / 32)];
+    __shared__ double accs[SMEMACC ? 4 * THREADS : 4];
+    for (int e = threadIdx.x; e < N * N; e += THREADS) {
+        double2 v = reinterpret_cast<const double2 *>(A)[e];
+        sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
+    }
+    if (SMEMACC) { accs[threadIdx.x] = 0.0; accs[THREADS + threadIdx.x] = 0.0; accs[2 * THREADS + threadIdx.x] = 0.0; accs[3 * THREADS + threadIdx.x] = 0.0; }
+    __syncthreads();
+    const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    const uint64_t start = lo + gtid * span;
+    dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
+    if (start < hi) {
+        const uint64_t end = (hi - start < span) ? hi : start + span;
+        double sr[N], si[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+        const uint64_t g0 = start ^ (start >> 1);
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            const double sg = ((g0 >> i) & 1ull) ? -0.5 : 0.5;
+            const double2 *row = sA2 + i * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+        }
+        double wr = 0.0, wi = 0.0;
+        e6_prod_acc<true>(sr, si, wr, wi);
+#pragma unroll 1
+        for (uint64_t I0 = start;;) {
+            upd_const_fixed<0, false>(sr, si);
+            e6_prod_acc<false>(sr, si, wr, wi);
+            upd_const<1>(sr, si, ((I0 >> 2) & 1ull) ? 1.0 : -1.0);
+            e6_prod_acc<true>(sr, si, wr, wi);
+            upd_const_fixed<0, true>(sr, si);
+            e6_prod_acc<false>(sr, si, wr, wi);
+            I0 += 4;
+            if (I0 >= end) break;
+            if (((uint32_t)I0 & 63u) == 0u) {
+                if (SMEMACC) {
+                    dd a = {accs[threadIdx.x], accs[THREADS + threadIdx.x]}, b = {accs[2 * THREADS + threadIdx.x], accs[3 * THREADS + threadIdx.x]};
+                    a = dd_add_d(a, wr); b = dd_add_d(b, wi);
+                    accs[threadIdx.x] = a.hi; accs[THREADS + threadIdx.x] = a.lo; accs[2 * THREADS + threadIdx.x] = b.hi; accs[3 * THREADS + threadIdx.x] = b.lo;
+                } else { acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi); }
+                wr = 0.0; wi = 0.0;
+            }
+            const int r = ctz64(I0);
+            const double sg = ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0;
+            const double2 *row = sA2 + r * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+            e6_prod_acc<true>(sr, si, wr, wi);
+        }
+        if (SMEMACC) { acc_re.hi = accs[threadIdx.x]; acc_re.lo = accs[THREADS + threadIdx.x]; acc_im.hi = accs[2 * THREADS + threadIdx.x]; acc_im.lo = accs[3 * THREADS + threadIdx.x]; }
+        acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+    }
+    block_reduce_dd(acc_re, acc_im, red);
+    if (threadIdx.x == 0) { double *o = partials + 4 * (size_t)blockIdx.x; o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo; }
+}
+
+// variant E7: E6 with 32-bit loop bookkeeping
+template <int THREADS, bool SMEMACC>
+__global__ void __launch_bounds__(THREADS, 1)
+k1_e7(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span, double *__restrict__ partials) {
+    __shared__ double2 sA2[N * N];
+    __shared__ double red[4 * (THREADS / 32)];
+    __shared__ double accs[SMEMACC ? 4 * THREADS : 4];
+    for (int e = threadIdx.x; e < N * N; e += THREADS) {
+        double2 v = reinterpret_cast<const double2 *>(A)[e];
+        sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
+    }
+    if (SMEMACC) { accs[threadIdx.x] = 0.0; accs[THREADS + threadIdx.x] = 0.0; accs[2 * THREADS + threadIdx.x] = 0.0; accs[3 * THREADS + threadIdx.x] = 0.0; }
+    __syncthreads();
+    const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    const uint64_t start = lo + gtid * span;
+    dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
+    if (start < hi) {
+        const uint64_t end = (hi - start < span) ? hi : start + span;
+        double sr[N], si[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+        const uint64_t g0 = start ^ (start >> 1);
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            const double sg = ((g0 >> i) & 1ull) ? -0.5 : 0.5;
+            const double2 *row = sA2 + i * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+        }
+        double wr = 0.0, wi = 0.0;
+        e6_prod_acc<true>(sr, si, wr, wi);
+        // 32-bit bookkeeping: blocks count down; the low word of the step index gives row and sign unless it is 0
+        uint32_t nblk = (uint32_t)((end - start) >> 2);
+        uint32_t lo32 = (uint32_t)start, hi32 = (uint32_t)(start >> 32);
+#pragma unroll 1
+        for (;;) {
+            upd_const_fixed<0, false>(sr, si);
+            e6_prod_acc<false>(sr, si, wr, wi);
+            upd_const<1>(sr, si, (lo32 & 4u) ? 1.0 : -1.0);
+            e6_prod_acc<true>(sr, si, wr, wi);
+            upd_const_fixed<0, true>(sr, si);
+            e6_prod_acc<false>(sr, si, wr, wi);
+            lo32 += 4;
+            if (--nblk == 0) break;
+            if ((lo32 & 63u) == 0u) { acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi); wr = 0.0; wi = 0.0; }
+            int r; double sg;
+            if (lo32 & 0x7fffffffu) { r = __ffs((int)lo32) - 1; sg = ((lo32 >> (r + 1)) & 1u) ? 1.0 : -1.0; }
+            else {
+                if (lo32 == 0u) ++hi32;
+                const uint64_t I0 = ((uint64_t)hi32 << 32) | lo32;
+                r = ctz64(I0); sg = ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0;
+            }
+            const double2 *row = sA2 + r * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double2 a = row[j]; sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+            e6_prod_acc<true>(sr, si, wr, wi);
+        }
+        if (SMEMACC) { acc_re.hi = accs[threadIdx.x]; acc_re.lo = accs[THREADS + threadIdx.x]; acc_im.hi = accs[2 * THREADS + threadIdx.x]; acc_im.lo = accs[3 * THREADS + threadIdx.x]; }
+        acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+    }
+    block_reduce_dd(acc_re, acc_im, red);
+    if (threadIdx.x == 0) { double *o = partials + 4 * (size_t)blockIdx.x; o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // variant F: fully warp-uniform inner structure.  Every thread owns `nwin` whole 64-step windows;
 // inside a window the loop counters are block-uniform, so every flipped row (0..5) is addressed
@@ -1117,6 +1258,12 @@ int main(int argc, char **argv) {
         {"E4 nch3 256x1", k1_e4<3, 256, 1>, 256, 1, 1}, {"E4 nch2 384x1", k1_e4<2, 384, 1>, 384, 1, 1},
         {"E5 nch2 256x1", k1_e5<2, 256, 1>, 256, 1, 1}, {"E5 nch4 256x1", k1_e5<4, 256, 1>, 256, 1, 1},
         {"E5 nch3 256x1", k1_e5<3, 256, 1>, 256, 1, 1},
+        {"E nch1 u4 384x1", k1_e<1, 4, 384, 1>, 384, 1, 1}, {"E nch2 u4 384x1", k1_e<2, 4, 384, 1>, 384, 1, 1},
+        {"E nch1 u2 384x1", k1_e<1, 2, 384, 1>, 384, 1, 1}, {"E nch2 u2 384x1", k1_e<2, 2, 384, 1>, 384, 1, 1},
+        {"E nch1 u4 256x1", k1_e<1, 4, 256, 1>, 256, 1, 1},
+        {"E6 384 regacc", k1_e6<384, false>, 384, 1, 1}, {"E6 384 smemacc", k1_e6<384, true>, 384, 1, 1},
+        {"E6 256 regacc", k1_e6<256, false>, 256, 1, 1}, {"E6 512 smemacc", k1_e6<512, true>, 512, 1, 1},
+        {"E7 384 regacc", k1_e7<384, false>, 384, 1, 1},
         {"G u4 256x1", k1_g<4, 256, 1>, 256, 1, 1},  {"G u8 256x1", k1_g<8, 256, 1>, 256, 1, 1},  {"G u16 256x1", k1_g<16, 256, 1>, 256, 1, 1},
         {"G u2 256x1", k1_g<2, 256, 1>, 256, 1, 1},  {"G u4 384x1", k1_g<4, 384, 1>, 384, 1, 1},  {"G u8 384x1", k1_g<8, 384, 1>, 384, 1, 1},
         {"G u8 128x2", k1_g<8, 128, 2>, 128, 2, 1},  {"G u8 128x3", k1_g<8, 128, 3>, 128, 3, 1},  {"G u4 128x3", k1_g<4, 128, 3>, 128, 3, 1},

@@ -139,21 +139,37 @@ glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64
 // ---------------------------------------------------------------------------------------------
 #define K1B_MIN_N 23
 #define K1B_MAX_N 34
-#define K1B_THREADS 256
+
+// Per-N launch shape of the bulk kernel (measured at N = 30, profiles/r01_k1_explore.txt): three warps per SMSP
+// (384 threads, 168 registers) with a SINGLE product chain beat two warps (256 threads, 211 registers) with two
+// chains, 5.57 vs 5.85 ms; beyond N = 30 the column sums alone need more than 168 registers.
+template <int N>
+struct K1BCfg {
+    static constexpr int THREADS = (N <= 30) ? 384 : 256;
+    static constexpr int NCH = (N <= 30) ? 1 : 2;
+};
 
 __constant__ double2 c_A2[BP_MAX_N * BP_MAX_N];   // 2*A of the permanent in flight (row stride N)
 
-// product of the N column sums in two chains; the final chain-times-chain multiplication is fused into the
-// window accumulator (PLUS: w += p, else w -= p)
+// product of the N column sums in NCH (1 or 2) chains; the final multiplication is fused into the window
+// accumulator (PLUS: w += p, else w -= p): 4(N-2) + 4 FP64 instructions per step
 template <int N, bool PLUS>
 __device__ __forceinline__ void k1b_product_acc(const double (&sr)[N], const double (&si)[N], double &wr, double &wi) {
-    cplx p0 = {sr[0], si[0]}, p1 = {sr[1], si[1]};   // two chains measured best under the 255-register cap
+    if constexpr (K1BCfg<N>::NCH == 1) {
+        cplx p = {sr[0], si[0]};
 #pragma unroll
-    for (int j = 2; j < N; ++j) {
-        cplx s = {sr[j], si[j]};
-        if (j & 1) p1 = cmul(p1, s); else p0 = cmul(p0, s);
+        for (int j = 1; j < N - 1; ++j) { cplx s = {sr[j], si[j]}; p = cmul(p, s); }
+        cplx last = {sr[N - 1], si[N - 1]};
+        if (PLUS) cmul_acc(wr, wi, p, last); else cmul_sub(wr, wi, p, last);
+    } else {
+        cplx p0 = {sr[0], si[0]}, p1 = {sr[1], si[1]};
+#pragma unroll
+        for (int j = 2; j < N; ++j) {
+            cplx s = {sr[j], si[j]};
+            if (j & 1) p1 = cmul(p1, s); else p0 = cmul(p0, s);
+        }
+        if (PLUS) cmul_acc(wr, wi, p0, p1); else cmul_sub(wr, wi, p0, p1);
     }
-    if (PLUS) cmul_acc(wr, wi, p0, p1); else cmul_sub(wr, wi, p0, p1);
 }
 
 template <int N, int ROW, int MODE>   // MODE 0: subtract, 1: add, 2: run-time sign
@@ -169,17 +185,18 @@ __device__ __forceinline__ void k1b_flip_const(double (&sr)[N], double (&si)[N],
 // lo, hi and span are multiples of 64.  Reads the matrix twice: c_A2 (constant bank, rows 0-1 in
 // the loop) and A (global -> shared, run-time rows and the start state).
 template <int N>
-__global__ void __launch_bounds__(K1B_THREADS, 1)
+__global__ void __launch_bounds__(K1BCfg<N>::THREADS, 1)
 glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
                     double *__restrict__ partials) {
+    constexpr int THREADS = K1BCfg<N>::THREADS;
     __shared__ double2 sA2[N * N];
-    __shared__ double red[4 * (K1B_THREADS / 32)];
-    for (int e = threadIdx.x; e < N * N; e += K1B_THREADS) {
+    __shared__ double red[4 * (THREADS / 32)];
+    for (int e = threadIdx.x; e < N * N; e += THREADS) {
         double2 v = reinterpret_cast<const double2 *>(A)[e];
         sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
     }
     __syncthreads();
-    const uint64_t gtid = (uint64_t)blockIdx.x * K1B_THREADS + threadIdx.x;
+    const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
     const uint64_t start = lo + gtid * span;
     dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
     if (start < hi) {
@@ -268,16 +285,17 @@ __global__ void glynn_finish_kernel(const double *__restrict__ partials, int nbl
 // ---------------------------------------------------------------------------------------------
 typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *);
 
+static k1_fn g_k1_fn[BP_MAX_N + 1], g_k1_bulk[BP_MAX_N + 1];
+static int g_k1_minb[BP_MAX_N + 1], g_k1_bulk_threads[BP_MAX_N + 1];
+
 template <int N>
 static void k1_entry(k1_fn *fn, int *minb, k1_fn *bulk) {
     fn[N] = glynn_gray_kernel<N>;
     minb[N] = K1Cfg<N>::MINB;
-    if constexpr (N >= K1B_MIN_N && N <= K1B_MAX_N) bulk[N] = glynn_block4_kernel<N>;
+    if constexpr (N >= K1B_MIN_N && N <= K1B_MAX_N) { bulk[N] = glynn_block4_kernel<N>; g_k1_bulk_threads[N] = K1BCfg<N>::THREADS; }
     if constexpr (N > 1) k1_entry<N - 1>(fn, minb, bulk);
 }
 
-static k1_fn g_k1_fn[BP_MAX_N + 1], g_k1_bulk[BP_MAX_N + 1];
-static int g_k1_minb[BP_MAX_N + 1];
 static bool g_k1_init = false;
 
 // c_A2 is one slot per device: uses are ordered by a host mutex plus an event the next writer waits on.
@@ -327,10 +345,11 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
         if ((rc = bp_reserve(h, BP_SLOT_MISC, bytes + 64))) return rc;
         double *d_twice = (double *)h->d_buf[BP_SLOT_MISC];
         const uint64_t total = bhi - blo;
-        const uint64_t threads = (uint64_t)bulk_grid_max * K1B_THREADS;
+        const int bthreads = g_k1_bulk_threads[N];
+        const uint64_t threads = (uint64_t)bulk_grid_max * bthreads;
         uint64_t span = (total + threads - 1) / threads;
         span = ((span + 63) / 64) * 64;
-        const int grid = (int)(((total + span - 1) / span + K1B_THREADS - 1) / K1B_THREADS);
+        const int grid = (int)(((total + span - 1) / span + bthreads - 1) / bthreads);
         {
             std::lock_guard<std::mutex> g(g_const_mutex);
             if (!g_const_event_valid[h->device]) {
@@ -342,7 +361,7 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
             k1b_double_kernel<<<(2 * N * N + 255) / 256, 256, 0, h->stream>>>(dA, 2 * N * N, d_twice);
             BP_CHECK_LAUNCH(h);
             BP_CUDA(h, cudaMemcpyToSymbolAsync(c_A2, d_twice, bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
-            g_k1_bulk[N]<<<grid, K1B_THREADS, 0, h->stream>>>(dA, blo, bhi, span, d_partials);
+            g_k1_bulk[N]<<<grid, bthreads, 0, h->stream>>>(dA, blo, bhi, span, d_partials);
             BP_CHECK_LAUNCH(h);
             BP_CUDA(h, cudaEventRecord(g_const_event[h->device], h->stream));
         }
