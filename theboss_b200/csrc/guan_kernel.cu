@@ -82,12 +82,18 @@ __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, 
 template <int N>
 struct K2Cfg {
     static constexpr bool REGROW = (N <= K2_REGROW_MAX_N);
-    static constexpr int MINB = (N <= 8) ? 4 : (N <= 26) ? 3 : 2;
+#ifndef K2_MINB_MID
+#define K2_MINB_MID 3
+#endif
+#ifndef K2_NCH_MID
+#define K2_NCH_MID 1
+#endif
+    static constexpr int MINB = (N <= 8) ? 4 : (N <= 20) ? K2_MINB_MID : (N <= 26) ? 3 : 2;
 };
 
 template <int N>
 __device__ __forceinline__ void k2_product(const double (&sr)[N], const double (&si)[N], double &pr, double &pi) {
-    constexpr int NCH = (N > K2_REGROW_MAX_N) ? 4 : (N >= 4 ? 2 : 1);   // fewer chains where the inner row occupies registers
+    constexpr int NCH = (N > 20) ? 4 : (N > K2_REGROW_MAX_N) ? K2_NCH_MID : (N >= 4 ? 2 : 1);   // fewer chains where the inner row occupies registers
     cplx p[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { p[c].re = sr[c]; p[c].im = si[c]; }
