@@ -289,6 +289,51 @@ def secondary_metrics(device):
     return out
 
 
+def gccb_sampling_leg(world, rank, local_rank, per_rank=4096):
+    """Second half of the headline metric: GCC-B samples/s at n=24, m=48 (BASELINE configs[2] as a whole
+    sampling run).  Weak scaling: every rank draws `per_rank` samples of one job of per_rank * world samples
+    (contiguous slices, Philox keyed by the global sample index, no traffic until the final gather).  Timed on
+    the device (CUDA events on the handle's stream around the host-pointer call: H2D of U, 24 x (K3 + finish),
+    D2H of the samples), max over ranks; the gather of the (S, m) int32 result is timed separately by wall clock."""
+    import torch
+    import torch.distributed as dist
+
+    from theboss_b200 import _native
+    from theboss_b200.distributed import gather_samples, shard_bounds
+
+    n, m = 24, 48
+    U = workloads.haar(m, n)
+    s = np.array([1] * n + [0] * n, dtype=np.int32)
+    total = per_rank * world
+    lo, hi = shard_bounds(total, world, rank)
+    h = _native.default_handle(local_rank)
+    h.gccb_simulate(U, s, hi - lo, seed=1, first_sample=lo)          # warm-up at full size (scratch allocation)
+    best_ms, local = None, None
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = h.launch_count()
+        h.timer_start()
+        local = h.gccb_simulate(U, s, hi - lo, seed=5, first_sample=lo)
+        ms = h.timer_stop()
+        launches = h.launch_count() - launches0
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        best_ms = ms if best_ms is None else min(best_ms, ms)
+    t0 = time.perf_counter()
+    everything = gather_samples(torch.from_numpy(local).to(f"cuda:{local_rank}")).cpu().numpy()
+    gather_s = time.perf_counter() - t0
+    ok = everything.shape == (total, m) and bool((everything.sum(axis=1) == n).all())
+    return {"metric": "gcc_samples_per_s_n24_m48", "value": total / (best_ms * 1e-3), "unit": "samples/s", "samples": total,
+            "samples_per_rank": per_rank, "scaling": "weak", "ms": best_ms, "gpu_launches": int(launches),
+            "final_gather_s": gather_s, "particles_conserved": ok,
+            "note": "GeneralizedCliffordsBSimulationStrategy loop (K3 minors + finish kernel per step) on Haar(48, seed 24), "
+                    "input |1^24 0^24>; device time incl. H2D of U and D2H of the samples, max over ranks"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure
     Python (~2.3 h per n=30 permanent) and /root/reference does not exist on the
@@ -405,6 +450,8 @@ def run_native(args):
     e2e_ms = float(e2e_ms.item())
     assert result_e2e == result or abs(result_e2e - result) <= 1e-13 * abs(result)
 
+    sampling = gccb_sampling_leg(world, rank, local_rank)
+
     if rank == 0:
         # correctness gate on the timed result: long-double fixture of the same workload
         with open(os.path.join(REPO, "tests", "golden", "large_permanents.json")) as f:
@@ -437,6 +484,7 @@ def run_native(args):
             },
             "result": {"re": result.real, "im": result.imag, "rel_err_vs_long_double_fixture": rel},
             "wall_s_timed_region": wall1 - wall0,
+            "gcc_sampling": sampling,
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

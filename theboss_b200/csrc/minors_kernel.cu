@@ -28,7 +28,7 @@
 
 #include <stdlib.h>
 
-// shuffle inside one lane group only: groups of a warp may run different trip counts
+// xor-shuffle of a complex value; callers keep the trip counts warp-uniform and pass the full mask
 __device__ __forceinline__ cplx cshfl_xor(unsigned gmask, cplx a, int mask) {
     cplx r;
     r.re = __shfl_xor_sync(gmask, a.re, mask);
@@ -166,21 +166,25 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     const unsigned long long my_periods = pbase + (gidx < prem ? 1ull : 0ull);
     const unsigned long long row_start = (gidx * pbase + (gidx < prem ? gidx : prem)) * P;
     const unsigned long long rspan = my_periods * P;
+    // Trip counts are made WARP-uniform: the first group of a warp has the most periods (counts never grow with
+    // gidx); groups that own one period less run it as a dummy (weight 0, no stepping).  The butterfly can then
+    // use full-mask shuffles -- a per-group mask makes the compiler guard every shuffle with MATCH.ANY / VOTE /
+    // BRA.DIV, which cost 16 % of all issue-stall samples in the first version (profiles/r01_k3_n24_ncu_summary.txt).
+    const unsigned long long gidx_w = (unsigned long long)chunk * GROUPS + (threadIdx.x & ~31u) / LPG;
+    const unsigned long long warp_rows = (pbase + (gidx_w < prem ? 1ull : 0ull)) * P;
     const int col0 = lane_in_group * C;
-    const unsigned gmask = (LPG >= 32) ? 0xffffffffu : (((1u << LPG) - 1u) << ((threadIdx.x & 31) / LPG * LPG));
 
     double ar[C], ai[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) { ar[j] = 0.0; ai[j] = 0.0; }
 
-    // loop bounds are uniform inside a lane group and the shuffles are masked to the group, so
-    // groups of one warp may run different trip counts.
-    if (my_periods > 0) {
-        const unsigned long long row_end = row_start + rspan;
+    if (warp_rows > 0) {
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
+        st.dirmask = 0ull; st.binom = 0.0;
+        const bool mine = my_periods > 0;
         const unsigned long long hi0 = row_start / P;       // row_start is a multiple of P
-        guan_seek(item, hi0, r, st, /*v0=*/a_low + 1);      // digits above the table
+        if (mine) guan_seek(item, hi0, r, st, /*v0=*/a_low + 1);      // digits above the table
         int pos = (hi0 & 1ull) ? (int)P - 1 : 0;            // position inside the period (reflected)
         int pdir = (hi0 & 1ull) ? -1 : 1;
         unsigned off = 0;                                    // rows done in the current period
@@ -190,7 +194,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 #pragma unroll
         for (int j = 0; j < C; ++j) { cr[j] = 0.0; ci[j] = 0.0; }
         int par = r0;                                        // parity of sum(rho) -> sign of the term
-        {
+        if (mine) {
             unsigned q = (unsigned)pos;
 #pragma unroll 1
             for (int v = 0; v < D; ++v) {
@@ -219,48 +223,99 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
         }
         double sgn = (par & 1) ? -1.0 : 1.0;
-        double bout = st.binom * blow[pos];                  // binomial product of digits 1 .. D-1
+        double bout = mine ? st.binom * blow[pos] : 0.0;    // binomial product of digits 1 .. D-1 (0: dummy rows)
+        double w0 = bin0[r0];                                // weight of digit 0, fetched one term ahead
 
+        constexpr int H = (C >= 6) ? C / 2 : C;             // columns [0, H) and [H, C) form two independent chains
 #pragma unroll 1
-        for (unsigned long long q = row_start;;) {
+        for (unsigned long long q = 0;;) {
+            // ---- plan the step to the next row now, so that its table / digit loads overlap the sweep below
+            const bool have_next = q + 1 < warp_rows;
+            int v_next = 0;
+            double sg_next = 0.0, bout_next = 0.0;           // dummy rows: c stays, weight 0
+            if (have_next && q + 1 < rspan) {
+                int up;
+                if (++off < P) {
+                    // table step of the low digits (same for every group of the block)
+                    const int idx = (pdir > 0) ? pos + 1 : pos;
+                    const unsigned e = steptab[idx];
+                    v_next = (int)(e & 0xffu);
+                    up = (pdir > 0) ? (int)(e >> 8) : 1 - (int)(e >> 8);
+                    pos += pdir;
+                } else {
+                    // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
+                    int delta;
+                    v_next = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+                    up = delta > 0;
+                    off = 0;
+                    pdir = -pdir;
+                }
+                bout_next = st.binom * blow[pos];
+                sg_next = up ? -1.0 : 1.0;                   // c -= 2 * delta * X[v]
+            }
+            const double2 *row_next = X2 + v_next * W + col0;
             // ---- inner sweep over digit 0: L0 + 1 terms, no stepping logic, no row loads
 #pragma unroll 1
             for (int step = 0;; ++step) {
-                // prefix products over this lane's columns
+                const double w = sgn * bout * w0;
+                // prefix products over this lane's columns, one chain per half
                 cplx pre[C];
                 pre[0].re = 1.0; pre[0].im = 0.0;
-                if (C > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
+                if (H > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
 #pragma unroll
-                for (int j = 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
-                cplx tot;
-                if (C > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; tot = cmul(pre[C - 1], cl); }
-                else       { tot.re = cr[0]; tot.im = ci[0]; }
+                for (int j = 2; j < H; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
+                cplx totA, totB = {1.0, 0.0};
+                if (H > 1) { cplx cl = {cr[H - 1], ci[H - 1]}; totA = cmul(pre[H - 1], cl); }
+                else       { totA.re = cr[0]; totA.im = ci[0]; }
+                if (H < C) {
+                    pre[H].re = 1.0; pre[H].im = 0.0;
+                    if (C - H > 1) { pre[H + 1].re = cr[H]; pre[H + 1].im = ci[H]; }
+#pragma unroll
+                    for (int j = H + 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
+                    if (C - H > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; totB = cmul(pre[C - 1], cl); }
+                    else           { totB.re = cr[C - 1]; totB.im = ci[C - 1]; }
+                }
                 // product of the other lanes' totals (xor butterfly inside the group)
                 cplx oth = {1.0, 0.0};
                 if (LPG > 1) {
-                    cplx all = tot;
+                    cplx all = (H < C) ? cmul(totA, totB) : totA;
 #pragma unroll
                     for (int mask = 1; mask < LPG; mask <<= 1) {
-                        const cplx x = cshfl_xor(gmask, all, mask);
+                        const cplx x = cshfl_xor(0xffffffffu, all, mask);
                         oth = (mask == 1) ? x : cmul(oth, x);
                         if ((mask << 1) < LPG) all = cmul(all, x);
                     }
                 }
-                const double w = sgn * bout * bin0[r0];
-                cplx suf = {w * oth.re, w * oth.im};
-                // suffix pass: leave-one-out products, accumulate
+                cplx seed = {w * oth.re, w * oth.im};
+                // next value of digit 0 (its weight is needed one term ahead)
+                const bool last = (step == L0);
+                if (!last) r0 += dir0;
+                w0 = bin0[r0];
+                // suffix passes: leave-one-out products, accumulated; the two halves seed each other's totals
+                if (H < C) {
+                    cplx sufB = cmul(seed, totA);
 #pragma unroll
-                for (int j = C - 1; j >= 0; --j) {
-                    if (j == 0) { ar[0] += suf.re; ai[0] += suf.im; }
-                    else {
-                        cmul_acc(ar[j], ai[j], pre[j], suf);          // acc_j += prefix_j * suffix_j, fused
-                        cplx cj = {cr[j], ci[j]};
-                        suf = cmul(suf, cj);
+                    for (int j = C - 1; j >= H; --j) {
+                        if (j == H) { ar[H] += sufB.re; ai[H] += sufB.im; }
+                        else {
+                            cmul_acc(ar[j], ai[j], pre[j], sufB);
+                            cplx cj = {cr[j], ci[j]};
+                            sufB = cmul(sufB, cj);
+                        }
                     }
                 }
-                if (step == L0) break;
-                // next value of digit 0: c -= 2 * dir0 * X[0]
-                r0 += dir0;
+                cplx sufA = (H < C) ? cmul(seed, totB) : seed;
+#pragma unroll
+                for (int j = H - 1; j >= 0; --j) {
+                    if (j == 0) { ar[0] += sufA.re; ai[0] += sufA.im; }
+                    else {
+                        cmul_acc(ar[j], ai[j], pre[j], sufA);          // acc_j += prefix_j * suffix_j, fused
+                        cplx cj = {cr[j], ci[j]};
+                        sufA = cmul(sufA, cj);
+                    }
+                }
+                if (last) break;
+                // c -= 2 * dir0 * X[0]
                 sgn = -sgn;
                 const double sg = (dir0 > 0) ? -1.0 : 1.0;
 #pragma unroll
@@ -268,33 +323,15 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             }
             dir0 = -dir0;
             // ---- next row
-            if (++q >= row_end) break;
-            int v, up;
-            if (++off < P) {
-                // table step of the low digits (same for every group of the block)
-                const int idx = (pdir > 0) ? pos + 1 : pos;
-                const unsigned e = steptab[idx];
-                v = (int)(e & 0xffu);
-                up = (pdir > 0) ? (int)(e >> 8) : 1 - (int)(e >> 8);
-                pos += pdir;
-                bout = st.binom * blow[pos];
-            } else {
-                // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
-                int delta;
-                v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
-                up = delta > 0;
-                off = 0;
-                pdir = -pdir;
-                bout = st.binom * blow[pos];
-            }
+            if (!have_next) break;
+            ++q;
             sgn = -sgn;
-            const double sg = up ? -1.0 : 1.0;               // c -= 2 * delta * X[v]
-            const double2 *row = X2 + v * W + col0;
+            bout = bout_next;
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                const double2 a = row[j];
-                cr[j] = fma(sg, a.x, cr[j]);
-                ci[j] = fma(sg, a.y, ci[j]);
+                const double2 a = row_next[j];
+                cr[j] = fma(sg_next, a.x, cr[j]);
+                ci[j] = fma(sg_next, a.y, ci[j]);
             }
         }
     }
