@@ -36,6 +36,24 @@ __device__ __forceinline__ cplx cshfl_xor(unsigned gmask, cplx a, int mask) {
     return r;
 }
 
+// 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset
+template <int OFF>
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+// c[j] += sg * X2row[j] for the C columns of a lane (row given by its shared-window address)
+template <int C, int J = 0>
+__device__ __forceinline__ void k3_row_update(unsigned row, double sg, double (&cr)[C], double (&ci)[C]) {
+    if constexpr (J < C) {
+        const double2 a = lds_f64x2<J * (int)sizeof(double2)>(row);
+        cr[J] = fma(sg, a.x, cr[J]);
+        ci[J] = fma(sg, a.y, ci[J]);
+        k3_row_update<C, J + 1>(row, sg, cr, ci);
+    }
+}
+
 // dynamic shared memory carve-up (bytes)
 __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
     size_t x2 = (size_t)rows * W * sizeof(double2);
@@ -50,6 +68,7 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
 // `active` exit at once; the finish kernel applies the same rule.
 #define K3_TERMS_PER_GROUP 192ull
 #define K3_PMAX 512
+struct __align__(16) K3Step { double blow; int off; int pad; };
 __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, int groups) {
     const unsigned long long per_block = K3_TERMS_PER_GROUP * (unsigned long long)groups;
     unsigned long long a = (terms + per_block - 1) / per_block;
@@ -84,8 +103,10 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 
     const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
     __shared__ double bin0[BP_MAX_N + 2];      // weight table of the inner digit: C(w_0, r) (x top weight if it is the only digit)
-    __shared__ double blow[K3_PMAX];           // binomial product of the low digits at period position p
-    __shared__ unsigned short steptab[K3_PMAX];// transition p-1 -> p of the low digits: digit | (delta > 0) << 8
+    // step tables of the low digits, indexed by the DESTINATION position p inside a period: binomial product of the
+    // low digits at p plus the transition that leads there (row byte offset of the changed digit, bit 0 = digit went
+    // up); fwd: from p - 1, bwd: from p + 1 (reflected periods).  One 16-byte load per row step.
+    __shared__ K3Step fwd[K3_PMAX], bwd[K3_PMAX];
     __shared__ int low_digits;                 // digits 1 .. low_digits are driven by the table
     __shared__ unsigned period;                // P = prod_{v=1..low_digits} (lim_v + 1): rows per table period
     if (threadIdx.x == 0) {
@@ -153,8 +174,11 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             if (v == D - 1) c *= gw_top_weight(item, rv);
             bprod *= c;
         }
-        blow[p] = bprod;
-        steptab[p] = (unsigned short)(chg | (up << 8));
+        const int rowbytes = W * (int)sizeof(double2);
+        fwd[p].blow = bprod; fwd[p].off = chg * rowbytes | up; fwd[p].pad = 0;
+        bwd[p].blow = bprod;
+        if (p == P - 1) { bwd[p].off = 0; bwd[p].pad = 0; }
+        if (p) { bwd[p - 1].off = chg * rowbytes | (up ^ 1); bwd[p - 1].pad = 0; }
     }
     __syncthreads();
 
@@ -171,7 +195,9 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     // use full-mask shuffles -- a per-group mask makes the compiler guard every shuffle with MATCH.ANY / VOTE /
     // BRA.DIV, which cost 16 % of all issue-stall samples in the first version (profiles/r01_k3_n24_ncu_summary.txt).
     const unsigned long long gidx_w = (unsigned long long)chunk * GROUPS + (threadIdx.x & ~31u) / LPG;
-    const unsigned long long warp_rows = (pbase + (gidx_w < prem ? 1ull : 0ull)) * P;
+    // (per-group row counts fit 32 bits: at most 2^39 terms over >= 16 groups x active chunks, see bp_k3_chunks)
+    const unsigned warp_rows = (unsigned)((pbase + (gidx_w < prem ? 1ull : 0ull)) * P);
+    const unsigned my_rows = (unsigned)rspan;
     const int col0 = lane_in_group * C;
 
     double ar[C], ai[C];
@@ -223,37 +249,42 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
         }
         double sgn = (par & 1) ? -1.0 : 1.0;
-        double bout = mine ? st.binom * blow[pos] : 0.0;    // binomial product of digits 1 .. D-1 (0: dummy rows)
+        double bout = mine ? st.binom * fwd[pos].blow : 0.0;    // binomial product of digits 1 .. D-1 (0: dummy rows)
+        const K3Step *tab = (pdir > 0) ? fwd : bwd;
+        // shared-window address of this lane's first column; kept opaque so that the row loads below use ONE address
+        // register plus immediates (the compiler otherwise hoists a separate pointer per column and spills)
+        unsigned x2c0 = (unsigned)__cvta_generic_to_shared(X2 + col0);
+        asm volatile("" : "+r"(x2c0));
         double w0 = bin0[r0];                                // weight of digit 0, fetched one term ahead
 
         constexpr int H = (C >= 6) ? C / 2 : C;             // columns [0, H) and [H, C) form two independent chains
 #pragma unroll 1
-        for (unsigned long long q = 0;;) {
+        for (unsigned q = 0;;) {
             // ---- plan the step to the next row now, so that its table / digit loads overlap the sweep below
             const bool have_next = q + 1 < warp_rows;
-            int v_next = 0;
-            double sg_next = 0.0, bout_next = 0.0;           // dummy rows: c stays, weight 0
-            if (have_next && q + 1 < rspan) {
-                int up;
+            int off_next = 0;                                // row byte offset of the digit that changes | went up
+            double bout_next = 0.0;                          // dummy rows: weight 0 (and sg_next = 0: c stays)
+            const bool real_next = q + 1 < my_rows;
+            if (real_next) {
                 if (++off < P) {
                     // table step of the low digits (same for every group of the block)
-                    const int idx = (pdir > 0) ? pos + 1 : pos;
-                    const unsigned e = steptab[idx];
-                    v_next = (int)(e & 0xffu);
-                    up = (pdir > 0) ? (int)(e >> 8) : 1 - (int)(e >> 8);
                     pos += pdir;
+                    const K3Step e = tab[pos];
+                    off_next = e.off;
+                    bout_next = st.binom * e.blow;
                 } else {
                     // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
                     int delta;
-                    v_next = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
-                    up = delta > 0;
+                    const int v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+                    off_next = v * (W * (int)sizeof(double2)) | (delta > 0 ? 1 : 0);
                     off = 0;
                     pdir = -pdir;
+                    tab = (pdir > 0) ? fwd : bwd;
+                    bout_next = st.binom * fwd[pos].blow;
                 }
-                bout_next = st.binom * blow[pos];
-                sg_next = up ? -1.0 : 1.0;                   // c -= 2 * delta * X[v]
             }
-            const double2 *row_next = X2 + v_next * W + col0;
+            const double sg_next = real_next ? ((off_next & 1) ? -1.0 : 1.0) : 0.0;   // c -= 2 * delta * X[v]
+            const unsigned row_next = x2c0 + (unsigned)(off_next & ~1);
             // ---- inner sweep over digit 0: L0 + 1 terms, no stepping logic, no row loads
 #pragma unroll 1
             for (int step = 0;; ++step) {
@@ -327,12 +358,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             ++q;
             sgn = -sgn;
             bout = bout_next;
-#pragma unroll
-            for (int j = 0; j < C; ++j) {
-                const double2 a = row_next[j];
-                cr[j] = fma(sg_next, a.x, cr[j]);
-                ci[j] = fma(sg_next, a.y, ci[j]);
-            }
+            k3_row_update<C>(row_next, sg_next, cr, ci);
         }
     }
 
@@ -526,7 +552,7 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
     if (k - 1 > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k - 1 <= %d, got k = %d", BP_MAX_N, k);
     if (samples > 65535) return bp_fail(h, BP_ERR_INVALID, "bp_k3_launch: at most 65535 samples per launch");
     const size_t smem = k3_smem_bytes(k - 1, v.lpg * v.c, v.c);
-    if (smem > 48 * 1024) {
+    if (smem > 24 * 1024) {   // static shared memory (step tables) takes ~17 KB of the 48 KB that need no opt-in
         cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
