@@ -75,6 +75,27 @@ __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, 
 // main kernel
 // ---------------------------------------------------------------------------------------------
 #define K2_PMAX 512
+struct __align__(16) K2Step { double blow; int off; int pad; };   // binomial product at the position; row byte offset | went-up bit
+
+// 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset
+// (PIN: volatile, so that loads of a loop-invariant row stay inside the term loop instead of occupying registers)
+template <int OFF, bool PIN>
+__device__ __forceinline__ double2 k2_lds(unsigned addr) {
+    double2 v;
+    if (PIN) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    else     asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+// sums[j] += sg * X2row[j], j = 0 .. N-1 (row given by its shared-window address: one register + immediates)
+template <int N, bool PIN, int J = 0>
+__device__ __forceinline__ void k2_row_update(unsigned row, double sg, double (&sr)[N], double (&si)[N]) {
+    if constexpr (J < N) {
+        const double2 a = k2_lds<J * (int)sizeof(double2), PIN>(row);
+        sr[J] = fma(sg, a.x, sr[J]);
+        si[J] = fma(sg, a.y, si[J]);
+        k2_row_update<N, PIN, J + 1>(row, sg, sr, si);
+    }
+}
 #ifndef K2_REGROW_MAX_N
 #define K2_REGROW_MAX_N 12   // up to this N the row of the inner digit is kept in registers (4N extra registers); measured at N=20: 3 warps/SMSP with LDS rows beat 2 warps with register rows (11.8 vs 12.3 ms on config 2)
 #endif
@@ -109,12 +130,6 @@ __device__ __forceinline__ void k2_product(const double (&sr)[N], const double (
     pr = p[0].re; pi = p[0].im;
 }
 
-// shared-memory load the compiler may not hoist out of the term loop (keeps the inner row out of registers for large N)
-__device__ __forceinline__ double2 k2_lds_nohoist(const double2 *p) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
-    return v;
-}
 
 // The walk of one item is organised like the minors kernel's (minors_kernel.cu): rows of L0 + 1 terms that
 // differ only in the inner digit 0 (largest multiplicity; swept up on even rows, down on odd ones), rows
@@ -132,8 +147,8 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     __shared__ unsigned char rdig[N * GW_THREADS];      // per-thread digit vectors (column = thread)
     __shared__ double red[4 * (GW_THREADS / 32)];
     __shared__ double bin0[BP_MAX_N + 2];
-    __shared__ double blow[K2_PMAX];
-    __shared__ unsigned short steptab[K2_PMAX];
+    // step tables of the low digits, indexed by the DESTINATION position inside a period (see minors_kernel.cu)
+    __shared__ K2Step fwd[K2_PMAX], bwd[K2_PMAX];
     __shared__ int low_digits;
     __shared__ unsigned period;
 
@@ -191,8 +206,11 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
             if (v == D - 1) c *= gw_top_weight(item, rv);
             bprod *= c;
         }
-        blow[p] = bprod;
-        steptab[p] = (unsigned short)(chg | (up << 8));
+        const int rowbytes = N * (int)sizeof(double2);
+        fwd[p].blow = bprod; fwd[p].off = chg * rowbytes | up; fwd[p].pad = 0;
+        bwd[p].blow = bprod;
+        if (p == P - 1) { bwd[p].off = 0; bwd[p].pad = 0; }
+        if (p) { bwd[p - 1].off = chg * rowbytes | (up ^ 1); bwd[p - 1].pad = 0; }
     }
     __syncthreads();
 
@@ -205,7 +223,7 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
 
     if (my_periods > 0) {
-        const unsigned long long row_end = row_start + my_periods * P;
+        const unsigned my_rows = (unsigned)(my_periods * P);   // per-thread row counts fit 32 bits (<= 2^39 terms over >= 128 threads)
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
         const unsigned long long hi0 = row_start / P;
@@ -247,18 +265,43 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
             for (int j = 0; j < N; ++j) { const double2 a = X2[j]; x0r[j] = a.x; x0i[j] = a.y; }
         }
         double sgn = (par & 1) ? -1.0 : 1.0;
-        double bout = st.binom * blow[pos];
+        double bout = st.binom * fwd[pos].blow;
+        const K2Step *tab = (pdir > 0) ? fwd : bwd;
+        // shared-window address of X2, kept opaque so that row loads use ONE address register plus immediates
+        unsigned x2base = (unsigned)__cvta_generic_to_shared(X2);
+        asm volatile("" : "+r"(x2base));
+        double w0 = bin0[r0];                                // weight of digit 0, fetched one term ahead
         double wr = 0.0, wi = 0.0;
         unsigned cnt = 0;
 
 #pragma unroll 1
-        for (unsigned long long q = row_start;;) {
+        for (unsigned q = 0;;) {
+            // ---- plan the step to the next row now, so that its table / digit loads overlap the sweep below
+            const bool have_next = q + 1 < my_rows;
+            int off_next = 0;
+            double bout_next = 0.0;
+            if (have_next) {
+                if (++off < P) {
+                    pos += pdir;
+                    const K2Step e = tab[pos];
+                    off_next = e.off;
+                    bout_next = st.binom * e.blow;
+                } else {
+                    int delta;
+                    const int v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+                    off_next = v * (N * (int)sizeof(double2)) | (delta > 0 ? 1 : 0);
+                    off = 0;
+                    pdir = -pdir;
+                    tab = (pdir > 0) ? fwd : bwd;
+                    bout_next = st.binom * fwd[pos].blow;
+                }
+            }
             // ---- inner sweep over digit 0
 #pragma unroll 1
             for (int step = 0;; ++step) {
+                const double w = sgn * bout * w0;
                 double pr, pi;
                 k2_product<N>(sr, si, pr, pi);
-                const double w = sgn * bout * bin0[r0];
                 wr = fma(w, pr, wr);
                 wi = fma(w, pi, wi);
                 if (++cnt == 64u) {
@@ -266,46 +309,26 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
                     acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
                     wr = 0.0; wi = 0.0;
                 }
-                if (step == L0) break;
-                r0 += dir0;
+                const bool last = (step == L0);
+                if (!last) r0 += dir0;
+                w0 = bin0[r0];
+                if (last) break;
                 sgn = -sgn;
                 const double sg = (dir0 > 0) ? -1.0 : 1.0;        // sums -= 2 * dir0 * X[0]
                 if (REGROW) {
 #pragma unroll
                     for (int j = 0; j < N; ++j) { sr[j] = fma(sg, x0r[j], sr[j]); si[j] = fma(sg, x0i[j], si[j]); }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) { const double2 a = k2_lds_nohoist(X2 + j); sr[j] = fma(sg, a.x, sr[j]); si[j] = fma(sg, a.y, si[j]); }
+                    k2_row_update<N, true>(x2base, sg, sr, si);
                 }
             }
             dir0 = -dir0;
             // ---- next row
-            if (++q >= row_end) break;
-            int v, up;
-            if (++off < P) {
-                const int idx = (pdir > 0) ? pos + 1 : pos;
-                const unsigned e = steptab[idx];
-                v = (int)(e & 0xffu);
-                up = (pdir > 0) ? (int)(e >> 8) : 1 - (int)(e >> 8);
-                pos += pdir;
-                bout = st.binom * blow[pos];
-            } else {
-                int delta;
-                v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
-                up = delta > 0;
-                off = 0;
-                pdir = -pdir;
-                bout = st.binom * blow[pos];
-            }
+            if (!have_next) break;
+            ++q;
             sgn = -sgn;
-            const double sg = up ? -1.0 : 1.0;
-            const double2 *row = X2 + v * N;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 a = row[j];
-                sr[j] = fma(sg, a.x, sr[j]);
-                si[j] = fma(sg, a.y, si[j]);
-            }
+            bout = bout_next;
+            k2_row_update<N, false>(x2base + (unsigned)(off_next & ~1), (off_next & 1) ? -1.0 : 1.0, sr, si);   // sums -= 2 * delta * X[v]
         }
         acc_re = dd_add_d(acc_re, wr);
         acc_im = dd_add_d(acc_im, wi);
