@@ -6,7 +6,7 @@ struct K3Finish {
     const double *U; size_t u_stride;                          // per-sample matrix stride in doubles (0 = shared)
     int m; int W; int chunks; int step;                        // step = k - 1 (0-based)
     const double *partials;
-    const unsigned long long *terms; int groups;               // per-sample walk length (written by K3), lane groups per block
+    const unsigned long long *terms; unsigned long long per_block; // per-sample walk length (written by K3), terms served by one chunk block
     unsigned char *occ_s, *occ_t;                              // [samples][m]
     double *minors_out;                                        // NULL or [samples][m] complex
     double *pmf_out;                                           // NULL or [samples][m]
@@ -18,7 +18,7 @@ struct K3Finish {
 
 int bp_k3_width(int k);
 int bp_k3_chunks(bp_context *h, int k, long long samples);
-int bp_k3_groups(int k);
+unsigned long long bp_k3_per_block(bp_context *h, int k, long long samples);
 int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const unsigned char *d_s, const unsigned char *d_t,
                  const int *d_steps_total, int k, long long samples, int chunks, double *d_partials,
                  unsigned long long *d_terms);

@@ -69,8 +69,7 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
 #define K3_TERMS_PER_GROUP 192ull
 #define K3_PMAX 512
 struct __align__(16) K3Step { double blow; int off; int pad; };
-__host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, int groups) {
-    const unsigned long long per_block = K3_TERMS_PER_GROUP * (unsigned long long)groups;
+__host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, unsigned long long per_block) {
     unsigned long long a = (terms + per_block - 1) / per_block;
     if (a < 1) a = 1;
     if (a > (unsigned long long)chunks) a = (unsigned long long)chunks;
@@ -89,7 +88,7 @@ template <int LPG, int C>
 __global__ void __launch_bounds__(GW_THREADS, K3Cfg<LPG, C>::MINB)
 k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const unsigned char *__restrict__ occ_s,
                  const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, int step,
-                 double *__restrict__ partials, unsigned long long *__restrict__ terms_out) {
+                 double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
     constexpr int W = LPG * C;
     constexpr int GROUPS = GW_THREADS / LPG;
     extern __shared__ __align__(16) unsigned char k3_smem[];
@@ -121,7 +120,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     }
     __syncthreads();
     const int D = item.D;
-    const int active = k3_active_chunks(item.terms, chunks, GROUPS);
+    const int active = k3_active_chunks(item.terms, chunks, per_block);
     if (chunk == 0 && threadIdx.x == 0) terms_out[sample] = item.terms;
     if (chunk >= active) return;
     double2 *X2 = reinterpret_cast<double2 *>(k3_smem);
@@ -409,7 +408,7 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
         } else if (first_col[v] >= 0) {
             dd re = {0.0, 0.0}, im = {0.0, 0.0};
             const double *base = a.partials + ((size_t)sample * a.chunks) * (size_t)(a.W * 4) + 4 * (int)first_col[v];
-            const int active = k3_active_chunks(a.terms[sample], a.chunks, a.groups);
+            const int active = k3_active_chunks(a.terms[sample], a.chunks, a.per_block);
             for (int ch = 0; ch < active; ++ch) {   // fixed chunk order
                 const double *q = base + (size_t)ch * (a.W * 4);
                 dd x = {q[0], q[1]}, y = {q[2], q[3]};
@@ -476,7 +475,7 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *);
+typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *, unsigned long long);
 
 struct K3Variant { k3_fn fn; int lpg, c; };
 #define K3_MAX_C 12
@@ -523,23 +522,51 @@ static K3Variant k3_pick(int k) {
 }
 
 int bp_k3_width(int k) { K3Variant v = k3_pick(k); return v.fn ? v.lpg * v.c : 0; }
-int bp_k3_groups(int k) { K3Variant v = k3_pick(k); return v.fn ? GW_THREADS / v.lpg : GW_THREADS; }
-
-// chunk blocks launched per sample for step k over `samples` samples: sized for the collision-free
-// worst case of the walk (2^(k-2) terms) but not more than ~64 blocks per SM in total; blocks a sample
-// does not need exit immediately (k3_active_chunks).
-int bp_k3_chunks(bp_context *h, int k, long long samples) {
-    if (k <= 1) return 1;
+// Work sizing of step k over `samples` samples.  A sample whose walk has T terms is served by
+// ceil(T / per_block) chunk blocks (at most `chunks`, the launched grid width); the other blocks exit at once.
+//   * per_block = (terms per lane group) x (groups per block).  With few samples the target is 192 terms per
+//     group (parallelism first); with enough samples to fill the GPU anyway it grows to 2048, because every
+//     block pays ~18 us of setup and reduction (measured: +62 ns of kernel time per extra block at 4096 samples);
+//   * chunks is sized for the collision-free worst case 2^(k-2), capped so that the heaviest samples still split
+//     into blocks of bounded duration (tail of the launch) without flooding the grid with empty blocks.
+// BP_K3_TPG / BP_K3_CAP override the two knobs (tuning).
+static void k3_plan(bp_context *h, int k, long long samples, int *chunks_out, unsigned long long *per_block_out) {
+    static int env_tpg = -1, env_cap = -1;
+    if (env_tpg < 0) { const char *e = getenv("BP_K3_TPG"); env_tpg = e ? atoi(e) : 0; }
+    if (env_cap < 0) { const char *e = getenv("BP_K3_CAP"); env_cap = e ? atoi(e) : 0; }
     K3Variant v = k3_pick(k);
     const int groups = GW_THREADS / (v.lpg ? v.lpg : 1);
-    const double max_terms = ldexp(1.0, k - 2);
-    long long by_work = (long long)ceil(max_terms / (double)(K3_TERMS_PER_GROUP * groups));
-    if (by_work < 1) by_work = 1;
-    long long by_fill = ((long long)h->sm_count * 64 + samples - 1) / samples;
-    if (by_fill < 1) by_fill = 1;
-    long long ch = by_work < by_fill ? by_work : by_fill;
-    if (ch > 256) ch = 256;
-    return (int)ch;
+    const long long fill_blocks = (long long)h->sm_count * 8;
+    long long tpg = (long long)K3_TERMS_PER_GROUP;
+    if (samples >= fill_blocks) tpg = 2048;
+    else if (2048 * samples / fill_blocks > tpg) tpg = 2048 * samples / fill_blocks;
+    if (env_tpg > 0) tpg = env_tpg;
+    const unsigned long long per_block = (unsigned long long)tpg * (unsigned long long)groups;
+    int chunks = 1;
+    if (k > 1) {
+        const double max_terms = ldexp(1.0, k - 2);
+        long long by_work = (long long)ceil(max_terms / (double)per_block);
+        if (by_work < 1) by_work = 1;
+        long long by_fill = ((long long)h->sm_count * 64 + samples - 1) / samples;
+        const long long cap = env_cap > 0 ? env_cap : 16;   // measured optimum 8 .. 32 (profiles/r01_k3_sizing.txt)
+        if (by_fill < cap) by_fill = cap;
+        long long ch = by_work < by_fill ? by_work : by_fill;
+        if (ch > 256) ch = 256;
+        chunks = (int)ch;
+    }
+    *chunks_out = chunks;
+    *per_block_out = per_block;
+}
+
+int bp_k3_chunks(bp_context *h, int k, long long samples) {
+    int ch; unsigned long long pb;
+    k3_plan(h, k, samples, &ch, &pb);
+    return ch;
+}
+unsigned long long bp_k3_per_block(bp_context *h, int k, long long samples) {
+    int ch; unsigned long long pb;
+    k3_plan(h, k, samples, &ch, &pb);
+    return pb;
 }
 
 // Enqueue the minors main kernel for step k (= particles in occ_s) over `samples` samples.
@@ -557,7 +584,8 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
         if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)chunks, (unsigned)samples);
-    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms);
+    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms,
+                                                bp_k3_per_block(h, k, samples));
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }

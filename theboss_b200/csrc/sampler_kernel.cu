@@ -147,7 +147,7 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     K3Finish a;
     memset(&a, 0, sizeof(a));
     a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = (int)k - 1; a.partials = d_part;
-    a.terms = d_terms; a.groups = bp_k3_groups((int)k);
+    a.terms = d_terms; a.per_block = bp_k3_per_block(h, (int)k, 1);
     a.occ_s = d_s; a.occ_t = d_t; a.minors_out = d_min; a.pmf_out = pmf ? d_pmf : nullptr;
     if ((rc = bp_k3_finish_launch(h, a, 1))) return rc;
     double *hres = (double *)((char *)h->h_pin + ((2 * (size_t)m + 63) / 64) * 64);
@@ -272,7 +272,7 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
             K3Finish a;
             memset(&a, 0, sizeof(a));
             a.U = dU; a.u_stride = u_stride; a.m = m; a.W = W; a.chunks = chunks; a.step = k - 1; a.partials = d_part;
-            a.terms = d_terms; a.groups = bp_k3_groups(k);
+            a.terms = d_terms; a.per_block = bp_k3_per_block(h, k, S);
             a.occ_s = d_occ_s; a.occ_t = d_occ_t;
             a.tape = d_tape; a.tape_stride = stride; a.remaining = d_rem; a.n_remaining = d_nrem; a.n = n;
             a.steps_total = d_steps;
