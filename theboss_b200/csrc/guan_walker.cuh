@@ -102,8 +102,9 @@ __device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsig
     double b = 1.0;
     for (int v = v0; v < it.D; ++v) {
         const unsigned R = (unsigned)it.lim[v] + 1u;
-        const unsigned d = (unsigned)(q % R);
-        q /= R;
+        unsigned d;
+        if (q >> 32) { d = (unsigned)(q % R); q /= R; }                                   // 64-bit division: ~10x the cost, rare
+        else         { const unsigned q32 = (unsigned)q; d = q32 % R; q = q32 / R; }
         int rv;
         if (q & 1ull) { rv = (int)it.lim[v] - (int)d; st.dirmask |= (1ull << v); }
         else          { rv = (int)d; }

@@ -110,13 +110,14 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     __shared__ unsigned period;                // P = prod_{v=1..low_digits} (lim_v + 1): rows per table period
     if (threadIdx.x == 0) {
         guan_item_build(item, t, m, /*inner_first=*/true);
+        if (item.D > 0)
+            for (int r = 0; r <= (int)item.lim[0]; ++r)
+                bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
+    } else if (threadIdx.x == 32) {   // a second warp expands the input columns meanwhile
         int c = 0;
         for (int v = 0; v < m; ++v)
             for (int a = 0; a < s[v] && c < W; ++a) col_mode[c++] = (short)v;
         for (; c < W; ++c) col_mode[c] = -1;
-        if (item.D > 0)
-            for (int r = 0; r <= (int)item.lim[0]; ++r)
-                bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
     }
     __syncthreads();
     const int D = item.D;
@@ -262,7 +263,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             // ---- plan the step to the next row now, so that its table / digit loads overlap the sweep below
             const bool have_next = q + 1 < warp_rows;
             int off_next = 0;                                // row byte offset of the digit that changes | went up
-            double bout_next = 0.0;                          // dummy rows: weight 0 (and sg_next = 0: c stays)
+            double blow_next = 0.0;                          // dummy rows: weight 0 (and sg_next = 0: c stays)
             const bool real_next = q + 1 < my_rows;
             if (real_next) {
                 if (++off < P) {
@@ -270,7 +271,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
                     pos += pdir;
                     const K3Step e = tab[pos];
                     off_next = e.off;
-                    bout_next = st.binom * e.blow;
+                    blow_next = e.blow;                      // multiplied by st.binom after the sweep: hides the load
                 } else {
                     // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
                     int delta;
@@ -279,7 +280,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
                     off = 0;
                     pdir = -pdir;
                     tab = (pdir > 0) ? fwd : bwd;
-                    bout_next = st.binom * fwd[pos].blow;
+                    blow_next = fwd[pos].blow;
                 }
             }
             const double sg_next = real_next ? ((off_next & 1) ? -1.0 : 1.0) : 0.0;   // c -= 2 * delta * X[v]
@@ -356,7 +357,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             if (!have_next) break;
             ++q;
             sgn = -sgn;
-            bout = bout_next;
+            bout = st.binom * blow_next;
             k3_row_update<C>(row_next, sg_next, cr, ci);
         }
     }
@@ -367,12 +368,35 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 #pragma unroll
     for (int j = 0; j < C; ++j) red[(col0 + j) * GROUPS + group] = make_double2(ar[j], ai[j]);
     __syncthreads();
-    for (int c = threadIdx.x; c < W; c += GW_THREADS) {
-        dd re = {0.0, 0.0}, im = {0.0, 0.0};
-        for (int g = 0; g < GROUPS; ++g) {
-            const double2 x = red[c * GROUPS + g];
-            re = dd_add_d(re, x.x);
-            im = dd_add_d(im, x.y);
+    // PARTS threads per column: each adds a contiguous slice of the groups (double-double, group order), thread 0 of
+    // the column then adds the PARTS partial sums in slice order -- a fixed summation order, GROUPS / PARTS deep
+    constexpr int PARTS = (GW_THREADS / W) < 1 ? 1 : ((GW_THREADS / W) > 8 ? 8 : (GW_THREADS / W));
+    constexpr int SLICE = (GROUPS + PARTS - 1) / PARTS;
+    __shared__ double part_sum[GW_THREADS * 4];
+    {
+        const int c = threadIdx.x / PARTS, part = threadIdx.x % PARTS;
+        if (c < W) {
+            dd re = {0.0, 0.0}, im = {0.0, 0.0};
+            const int g1 = (part + 1) * SLICE < GROUPS ? (part + 1) * SLICE : GROUPS;
+            for (int g = part * SLICE; g < g1; ++g) {
+                const double2 x = red[c * GROUPS + g];
+                re = dd_add_d(re, x.x);
+                im = dd_add_d(im, x.y);
+            }
+            double *ps = part_sum + 4 * threadIdx.x;
+            ps[0] = re.hi; ps[1] = re.lo; ps[2] = im.hi; ps[3] = im.lo;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < W) {
+        const int c = threadIdx.x;
+        const double *ps = part_sum + 4 * (c * PARTS);
+        dd re = {ps[0], ps[1]}, im = {ps[2], ps[3]};
+#pragma unroll
+        for (int q = 1; q < PARTS; ++q) {
+            dd a = {ps[4 * q + 0], ps[4 * q + 1]}, b = {ps[4 * q + 2], ps[4 * q + 3]};
+            re = dd_add(re, a);
+            im = dd_add(im, b);
         }
         my_part[4 * c + 0] = re.hi; my_part[4 * c + 1] = re.lo;
         my_part[4 * c + 2] = im.hi; my_part[4 * c + 3] = im.lo;
