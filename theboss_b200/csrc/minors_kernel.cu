@@ -575,7 +575,9 @@ static void k3_plan(bp_context *h, int k, long long samples, int *chunks_out, un
         const long long cap = env_cap > 0 ? env_cap : 16;   // measured optimum 8 .. 32 (profiles/r01_k3_sizing.txt)
         if (by_fill < cap) by_fill = cap;
         long long ch = by_work < by_fill ? by_work : by_fill;
-        if (ch > 256) ch = 256;
+        // one full wave of two resident blocks per SM when a single sample has the GPU to itself
+        const long long wave = 2ll * h->sm_count;
+        if (ch > wave) ch = wave;
         chunks = (int)ch;
     }
     *chunks_out = chunks;
