@@ -78,7 +78,7 @@ __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int ch
 
 template <int LPG, int C>
 struct K3Cfg {
-    static constexpr int MINB = (C <= 5) ? 4 : (C <= 7) ? 3 : 2;
+    static constexpr int MINB = (C <= 5) ? 4 : (C <= 8) ? 3 : 2;
 };
 
 // grid = (chunks, samples).  occ_s / occ_t: [samples][m] uint8 occupations (current input with the
