@@ -412,16 +412,20 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 //      with the tape's u_choice (:107-110), r_sample[j] += 1, then the NEXT step's input particle:
 //      pop index floor(u_pick * #remaining) of the remaining input particles (:102-105).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
+#define K3F_THREADS 64
+__global__ void __launch_bounds__(K3F_THREADS) k3_finish_kernel(K3Finish a) {
     __shared__ double2 P[BP_MAX_MODES];
     __shared__ double wgt[BP_MAX_MODES];
     __shared__ short first_col[BP_MAX_MODES];
+    __shared__ double total_sh;
+    __shared__ int idx_sh;
     const int sample = blockIdx.x, m = a.m, k = a.step + 1;
     if (a.steps_total && a.step >= a.steps_total[sample]) return;
     unsigned char *s = a.occ_s + (size_t)sample * m, *t = a.occ_t + (size_t)sample * m;
     if (threadIdx.x == 0) {
         int c = 0;
         for (int v = 0; v < m; ++v) { first_col[v] = s[v] ? (short)c : (short)-1; c += s[v]; }
+        idx_sh = 0;
     }
     __syncthreads();
     const double scale = ldexp(1.0, -(k - 1));
@@ -451,9 +455,10 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         double re = 0.0, im = 0.0;
         for (int i = 0; i < m; ++i) {
-            if (!s[i]) continue;
+            if (first_col[i] < 0) continue;
             // permanent_added = s_i * P_i; permanent_added *= U[j][i]; permanent += permanent_added
-            const double sr = (double)s[i] * P[i].x, si = (double)s[i] * P[i].y;
+            const double cnt = (double)s[i];
+            const double sr = cnt * P[i].x, si = cnt * P[i].y;
             const double2 u = U2[j * m + i];
             re += __dsub_rn(__dmul_rn(sr, u.x), __dmul_rn(si, u.y));
             im += __dadd_rn(__dmul_rn(sr, u.y), __dmul_rn(si, u.x));
@@ -462,23 +467,37 @@ __global__ void __launch_bounds__(256) k3_finish_kernel(K3Finish a) {
         wgt[j] = ab * ab;
     }
     __syncthreads();
+    // the sums stay sequential (python sum() / numpy.cumsum order); the element-wise divisions run in parallel
     if (threadIdx.x == 0) {
         double total = 0.0;
-        for (int j = 0; j < m; ++j) total += wgt[j];            // python sum(): sequential
-        for (int j = 0; j < m; ++j) wgt[j] = wgt[j] / total;
+        for (int j = 0; j < m; ++j) total += wgt[j];
+        total_sh = total;
     }
     __syncthreads();
-    if (a.pmf_out)
-        for (int j = threadIdx.x; j < m; j += blockDim.x) a.pmf_out[(size_t)sample * m + j] = wgt[j];
+    const double total = total_sh;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double w = wgt[j] / total;
+        wgt[j] = w;
+        if (a.pmf_out) a.pmf_out[(size_t)sample * m + j] = w;
+    }
     if (!a.tape) return;
+    __syncthreads();
+    const double *tp = a.tape + (size_t)sample * a.tape_stride;
+    // numpy.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side='right')
     if (threadIdx.x == 0) {
-        const double *tp = a.tape + (size_t)sample * a.tape_stride;
-        // numpy.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side='right')
         double run = 0.0;
         for (int j = 0; j < m; ++j) { run += wgt[j]; wgt[j] = run; }
+    }
+    __syncthreads();
+    {
         const double last = wgt[m - 1], u = tp[2 + 2 * a.step];
-        int idx = 0;
-        for (int j = 0; j < m; ++j) if (wgt[j] / last <= u) idx = j + 1;
+        int mine = 0;
+        for (int j = threadIdx.x; j < m; j += blockDim.x) if (wgt[j] / last <= u) mine = j + 1;   // j ascending: last hit wins
+        if (mine) atomicMax(&idx_sh, mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int idx = idx_sh;
         if (idx >= m) idx = m - 1;
         t[idx] += 1;
         // next step's input particle
@@ -617,7 +636,7 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
 }
 
 int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples) {
-    k3_finish_kernel<<<(unsigned)samples, 256, 0, h->stream>>>(a);
+    k3_finish_kernel<<<(unsigned)samples, K3F_THREADS, 0, h->stream>>>(a);
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }
