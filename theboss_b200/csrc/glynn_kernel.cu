@@ -27,6 +27,7 @@
 //     cutting the loop from 66 to ~29 non-FP64 instructions per step lifts the FP64 pipe from
 //     70 % to 88 % busy (profiles/).
 #include <mutex>
+#include <stdlib.h>
 
 #include "bp_common.cuh"
 
@@ -324,7 +325,12 @@ static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint6
 int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_out_dd) {
     if (!g_k1_init) {
         std::lock_guard<std::mutex> g(g_const_mutex);
-        if (!g_k1_init) { k1_entry<BP_MAX_N>(g_k1_fn, g_k1_minb, g_k1_bulk); g_k1_init = true; }
+        if (!g_k1_init) {
+            k1_entry<BP_MAX_N>(g_k1_fn, g_k1_minb, g_k1_bulk);
+            if (const char *e = getenv("BP_K1_BULK_MAX_N"))   // tuning: generic kernel above this N
+                for (int n = atoi(e) + 1; n <= BP_MAX_N; ++n) if (n >= 1) g_k1_bulk[n] = nullptr;
+            g_k1_init = true;
+        }
     }
     if (N < 1 || N > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "K1 supports 1 <= N <= %d, got %d", BP_MAX_N, N);
     const uint64_t total_terms = 1ull << (N - 1);
