@@ -119,6 +119,22 @@ def test_philox_mode_is_deterministic_and_split_invariant(handle):
     assert np.all(a.sum(axis=1) == 5)
 
 
+@pytest.mark.parametrize("eta", [-1.0, 0.6])
+def test_large_batch_equals_the_same_job_cut_into_pieces(handle, eta):
+    """The block sizing of the minors kernel depends on the batch size (k3_plan: 192 .. 2048 terms per lane group);
+    the samples must not: a 4097-sample job equals the same job cut into three smaller calls."""
+    U = workloads.haar(12, 9)
+    s = np.array([1] * 7 + [0] * 5, dtype=np.int32)
+    total = 4097                                                # odd: the halves differ in size
+    whole = handle.gccb_simulate(U, s, total, eta=eta, seed=99)
+    cuts = [0, 1500, 3000, total]
+    parts = [handle.gccb_simulate(U, s, b - a, eta=eta, seed=99, first_sample=a) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert np.all(whole.sum(axis=1) <= 7)
+    if eta < 0:
+        assert np.all(whole.sum(axis=1) == 7)
+
+
 def test_sampler_statistics_against_exact_distribution(handle):
     """Same acceptance criterion as the reference's strategy tests
     (quantum_computations_utilities.py:95-127): TVD within sqrt((-ln delta + K ln 2) / (2N))."""
