@@ -413,43 +413,69 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 //      pop index floor(u_pick * #remaining) of the remaining input particles (:102-105).
 // ---------------------------------------------------------------------------------------------
 #define K3F_THREADS 64
-__global__ void __launch_bounds__(K3F_THREADS) k3_finish_kernel(K3Finish a) {
+#define K3F_PARTS 16
+__global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
     __shared__ double2 P[BP_MAX_MODES];
     __shared__ double wgt[BP_MAX_MODES];
     __shared__ short first_col[BP_MAX_MODES];
     __shared__ double total_sh;
     __shared__ int idx_sh;
+    // chunk reduction of a single sample that had the whole GPU (up to 296 chunk blocks): K3F_PARTS interleaved slices
+    // per column summed by different threads, then added in slice order (fixed order); batches (<= 32 chunks) use one slice
+    __shared__ short occ_mode[BP_MAX_N + 2], occ_col[BP_MAX_N + 2];
+    __shared__ int nocc_sh;
+    extern __shared__ double psum[];   // [(BP_MAX_N + 2) * parts * 4]: parts = K3F_PARTS for a lone sample, else 1 (host sizes it)
     const int sample = blockIdx.x, m = a.m, k = a.step + 1;
     if (a.steps_total && a.step >= a.steps_total[sample]) return;
     unsigned char *s = a.occ_s + (size_t)sample * m, *t = a.occ_t + (size_t)sample * m;
     if (threadIdx.x == 0) {
-        int c = 0;
-        for (int v = 0; v < m; ++v) { first_col[v] = s[v] ? (short)c : (short)-1; c += s[v]; }
+        int c = 0, nocc = 0;
+        for (int v = 0; v < m; ++v) {
+            first_col[v] = s[v] ? (short)c : (short)-1;
+            if (s[v] && nocc < BP_MAX_N + 2) { occ_mode[nocc] = (short)v; occ_col[nocc] = (short)c; ++nocc; }
+            c += s[v];
+        }
+        nocc_sh = nocc;
         idx_sh = 0;
     }
+    for (int v = threadIdx.x; v < m; v += blockDim.x) P[v] = make_double2(k == 1 ? (double)s[v] : 0.0, 0.0);
     __syncthreads();
-    const double scale = ldexp(1.0, -(k - 1));
-    for (int v = threadIdx.x; v < m; v += blockDim.x) {
-        double2 p = make_double2(0.0, 0.0);
-        if (k == 1) {
-            p.x = (double)s[v];
-        } else if (first_col[v] >= 0) {
+    if (k > 1) {
+        const double scale = ldexp(1.0, -(k - 1));
+        const int nocc = nocc_sh;
+        const int active = k3_active_chunks(a.terms[sample], a.chunks, a.per_block);
+        const int parts = (gridDim.x == 1 && active > 32) ? K3F_PARTS : 1;
+        const double *base = a.partials + ((size_t)sample * a.chunks) * (size_t)(a.W * 4);
+        for (int it = threadIdx.x; it < nocc * parts; it += blockDim.x) {
+            const int i = it / parts, p = it - i * parts;
+            const double *col = base + 4 * (int)occ_col[i];
             dd re = {0.0, 0.0}, im = {0.0, 0.0};
-            const double *base = a.partials + ((size_t)sample * a.chunks) * (size_t)(a.W * 4) + 4 * (int)first_col[v];
-            const int active = k3_active_chunks(a.terms[sample], a.chunks, a.per_block);
-            for (int ch = 0; ch < active; ++ch) {   // fixed chunk order
-                const double *q = base + (size_t)ch * (a.W * 4);
+            for (int ch = p; ch < active; ch += parts) {   // fixed chunk order
+                const double *q = col + (size_t)ch * (a.W * 4);
                 dd x = {q[0], q[1]}, y = {q[2], q[3]};
                 re = dd_add(re, x);
                 im = dd_add(im, y);
             }
-            p.x = (re.hi + re.lo) * scale;
-            p.y = (im.hi + im.lo) * scale;
+            double *ps = psum + 4 * it;
+            ps[0] = re.hi; ps[1] = re.lo; ps[2] = im.hi; ps[3] = im.lo;
         }
-        P[v] = p;
-        if (a.minors_out) { a.minors_out[2 * ((size_t)sample * m + v)] = p.x; a.minors_out[2 * ((size_t)sample * m + v) + 1] = p.y; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nocc; i += blockDim.x) {
+            const double *ps = psum + 4 * (i * parts);
+            dd re = {ps[0], ps[1]}, im = {ps[2], ps[3]};
+            for (int p = 1; p < parts; ++p) {
+                dd x = {ps[4 * p + 0], ps[4 * p + 1]}, y = {ps[4 * p + 2], ps[4 * p + 3]};
+                re = dd_add(re, x);
+                im = dd_add(im, y);
+            }
+            P[occ_mode[i]] = make_double2((re.hi + re.lo) * scale, (im.hi + im.lo) * scale);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    if (a.minors_out)
+        for (int v = threadIdx.x; v < m; v += blockDim.x) {
+            a.minors_out[2 * ((size_t)sample * m + v)] = P[v].x; a.minors_out[2 * ((size_t)sample * m + v) + 1] = P[v].y;
+        }
     if (!a.pmf_out && !a.tape) return;
     const double2 *U2 = reinterpret_cast<const double2 *>(a.U + (size_t)sample * a.u_stride);
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
@@ -636,7 +662,10 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
 }
 
 int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples) {
-    k3_finish_kernel<<<(unsigned)samples, K3F_THREADS, 0, h->stream>>>(a);
+    // a lone sample may have up to 2 x SM-count chunk partials per column to add: give its block more threads
+    const int threads = samples == 1 ? 512 : K3F_THREADS;
+    const size_t smem = sizeof(double) * 4 * (BP_MAX_N + 2) * (samples == 1 ? K3F_PARTS : 1);
+    k3_finish_kernel<<<(unsigned)samples, threads, smem, h->stream>>>(a);
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }
