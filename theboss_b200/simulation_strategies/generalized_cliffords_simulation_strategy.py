@@ -32,6 +32,8 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
         self.pmfs: Dict[Tuple[int, ...], np.ndarray] = {}
         self._substates: Dict[int, np.ndarray] = {}
         self._weights: Dict[int, np.ndarray] = {}
+        self._norms: Dict[int, np.ndarray] = {}
+        self._prefetched: Dict[Tuple[int, ...], np.ndarray] = {}
 
     def set_new_matrix(self, new_matrix) -> None:
         self._bs_permanent_calculator.matrix = new_matrix
@@ -46,7 +48,7 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
         groups: Dict[int, List[Tuple[int, ...]]] = {}
         for sub in product(*[range(v + 1) for v in s]):
             groups.setdefault(sum(sub), []).append(sub)
-        self._substates, self._weights = {}, {}
+        self._substates, self._weights, self._norms = {}, {}, {}
         for k, subs in groups.items():
             raw = []
             for sub in subs:
@@ -57,29 +59,75 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
                 raw.append(w)
             self._substates[k] = np.array(subs, dtype=np.uint8).reshape(len(subs), len(s))
             self._weights[k] = np.array(raw) / sum(raw)
+            self._norms[k] = np.array([np.prod([factorial(int(o)) for o in sub]) for sub in subs], dtype=np.float64) * factorial(k)
+        self._prefetched = {}
 
     def _layer_pmf(self, r_sample: Sequence[int]) -> np.ndarray:
         """Un-normalised pmf over the output mode of the next particle (:136-171)."""
+        return self._layer_pmfs([tuple(int(v) for v in r_sample)])[0]
+
+    def _layer_pmfs(self, r_samples: Sequence[Tuple[int, ...]]) -> List[np.ndarray]:
+        """The layers of several partial outputs from ONE batched K2 launch: layer (r_sample, k = sum + 1) needs the
+        m x C(n, k) permanents |perm(U; substate -> r_sample + e_j)|, combined per candidate mode j in the reference's
+        order (sequential sum over the substates, :146-155 / :224-247)."""
         U = _native.as_matrix(self._bs_permanent_calculator.matrix)
         m_modes = U.shape[0]
         m = len(self.input_state)
-        k = int(sum(r_sample)) + 1
-        subs, weights = self._substates[k], self._weights[k]
-        n_sub = subs.shape[0]
-        S = np.zeros((m * n_sub, m_modes), dtype=np.uint8)
-        T = np.zeros((m * n_sub, m_modes), dtype=np.uint8)
-        S[:, :m] = np.tile(subs, (m, 1))
-        T[:, :m] = np.asarray(r_sample, dtype=np.uint8)
-        T[np.arange(m * n_sub), np.repeat(np.arange(m), n_sub)] += 1
-        perms = _native.default_handle(self._device).perm_batched(U, S, T)
-        norm = np.array([np.prod([factorial(int(o)) for o in sub]) for sub in subs], dtype=np.float64) * factorial(k)
-        pmf = np.zeros(m)
-        for j in range(m):
-            acc = 0
-            for i in range(n_sub):
-                acc += abs(perms[j * n_sub + i]) ** 2 / norm[i] * weights[i]
-            pmf[j] = acc
-        return pmf
+        blocks_S, blocks_T, shapes = [], [], []
+        for r_sample in r_samples:
+            k = int(sum(r_sample)) + 1
+            subs = self._substates[k]
+            n_sub = subs.shape[0]
+            S = np.zeros((m * n_sub, m_modes), dtype=np.uint8)
+            T = np.zeros((m * n_sub, m_modes), dtype=np.uint8)
+            S[:, :m] = np.tile(subs, (m, 1))
+            T[:, :m] = np.asarray(r_sample, dtype=np.uint8)
+            T[np.arange(m * n_sub), np.repeat(np.arange(m), n_sub)] += 1
+            blocks_S.append(S); blocks_T.append(T); shapes.append((k, n_sub))
+        perms = _native.default_handle(self._device).perm_batched(U, np.concatenate(blocks_S), np.concatenate(blocks_T))
+        out, pos = [], 0
+        for k, n_sub in shapes:
+            p = perms[pos: pos + m * n_sub].reshape(m, n_sub)
+            pos += m * n_sub
+            mod = np.hypot(p.real, p.imag)               # scalar abs() semantics (numpy.abs on arrays rounds differently)
+            terms = mod * mod / self._norms[k] * self._weights[k]
+            # numpy.cumsum adds left to right like the reference's Python loop (numpy.sum would add pairwise)
+            out.append(np.cumsum(terms, axis=1)[:, -1].copy())
+        return out
+
+    # Layers are requested one at a time by the chain rule, but a K2 launch costs the same ~0.1 ms for one layer
+    # as for thousands of small permanents, so a miss also computes the descendants of the missing partial output,
+    # level by level, while the request stays below this many permanents.  Speculated layers wait in a private
+    # cache and enter ``self.pmfs`` (the reference's memo) only when the sampler actually visits them.
+    _PREFETCH_BUDGET = 200_000
+
+    def _pmf_for(self, key: Tuple[int, ...]) -> Tuple[np.ndarray, bool]:
+        """pmf of the layer of partial output ``key`` and whether it is new to ``self.pmfs``."""
+        if key in self.pmfs:
+            return self.pmfs[key], False
+        if key not in self._prefetched:
+            n, m = self.number_of_input_photons, len(self.input_state)
+            wanted, frontier, cost = [key], [key], m * self._substates[sum(key) + 1].shape[0]
+            while True:
+                depth = sum(frontier[0]) + 1                 # particles in the children
+                if depth >= n:
+                    break
+                children = set()
+                for y in frontier:
+                    for j in range(m):
+                        c = y[:j] + (y[j] + 1,) + y[j + 1:]
+                        if c not in self.pmfs and c not in self._prefetched:
+                            children.add(c)
+                level_cost = len(children) * m * self._substates[depth + 1].shape[0]
+                if not children or cost + level_cost > self._PREFETCH_BUDGET:
+                    break
+                frontier = sorted(children)
+                wanted += frontier
+                cost += level_cost
+            for y, pmf in zip(wanted, self._layer_pmfs(wanted)):
+                self._prefetched[y] = pmf
+        self.pmfs[key] = self._prefetched.pop(key)
+        return self.pmfs[key], True
 
     # -- sampling ----------------------------------------------------------------------------------
     def simulate(self, input_state: Sequence[int], samples_number: int = 1) -> List[Tuple[int, ...]]:
@@ -96,10 +144,7 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
     def _fill_r_sample(self) -> None:
         self.r_sample = [0 for _ in self.input_state]
         while self.number_of_input_photons > sum(self.r_sample):
-            key = tuple(self.r_sample)
-            if key not in self.pmfs:
-                self.pmfs[key] = self._layer_pmf(self.r_sample)
-            pmf = self.pmfs[key]
+            pmf, _ = self._pmf_for(tuple(self.r_sample))
             threshold = np.random.random() * sum(pmf)   # pmfs are not normalised (:253-255)
             running, index = 0, 0
             for p in pmf:

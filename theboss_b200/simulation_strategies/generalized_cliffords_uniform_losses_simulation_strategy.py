@@ -82,11 +82,9 @@ class GeneralizedCliffordsUniformLossesSimulationStrategy(GeneralizedCliffordsSi
         for _ in range(self.number_of_input_photons):
             if _stdlib_random.random() >= self._transmissivity:
                 continue
-            key = tuple(self.r_sample)
-            if key not in self.pmfs:
-                self.pmfs[key] = self._layer_pmf(self.r_sample)
-                self._record_layer(self.r_sample, self.pmfs[key])
-            pmf = self.pmfs[key]
+            pmf, new = self._pmf_for(tuple(self.r_sample))
+            if new:
+                self._record_layer(self.r_sample, pmf)
             threshold = np.random.random() * sum(pmf)
             running, index = 0, 0
             for p in pmf:
