@@ -73,7 +73,7 @@ class GeneralizedCliffordsBSimulationStrategy(SimulationStrategyInterface):
     def simulate(self, input_state: Sequence[int], samples_number: int = 1,
                  decision_tape: Optional[np.ndarray] = None) -> List[Tuple[int, ...]]:
         out = self._run(input_state, samples_number, decision_tape)
-        return [tuple(int(v) for v in row) for row in out]
+        return [tuple(row) for row in out.tolist()]   # Python ints, converted at C speed
 
     def compute_pmf(self, current_input: Sequence[int], r_sample: Sequence[int]) -> np.ndarray:
         """The pmf of one step (_compute_pmf, :69-92): probabilities of the next particle's output mode

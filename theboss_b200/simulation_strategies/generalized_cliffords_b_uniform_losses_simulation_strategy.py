@@ -29,4 +29,4 @@ class GeneralizedCliffordsBUniformLossesSimulationStrategy(GeneralizedCliffordsB
     def simulate(self, input_state, samples_number: int = 1,
                  decision_tape: Optional[np.ndarray] = None) -> List[np.ndarray]:
         out = self._run(input_state, samples_number, decision_tape)
-        return [np.array(row, dtype=np.int64) for row in out]
+        return list(out.astype(np.int64))   # one int64 row per sample, like the reference (:108)

@@ -51,4 +51,4 @@ class LossyStateApproximationSimulationStrategy(SimulationStrategyInterface):
         Us = (Us * phases[:, None, :]) @ qft
         seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
         out = _native.default_handle(self._device).gccb_simulate_batch(np.ascontiguousarray(Us), states, seed=seed)
-        return [tuple(int(x) for x in row) for row in out]
+        return [tuple(row) for row in out.tolist()]

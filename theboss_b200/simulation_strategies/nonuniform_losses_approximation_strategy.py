@@ -73,4 +73,4 @@ class NonuniformLossesApproximationStrategy:
         big_states[:, :m] = states
         seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
         out = _native.default_handle(self._device).gccb_simulate_batch(Us, big_states, seed=seed)
-        return [tuple(int(x) for x in row[:m]) for row in out]
+        return [tuple(row) for row in out[:, :m].tolist()]
