@@ -96,6 +96,8 @@ __device__ __forceinline__ double gw_top_weight(const GuanItem &it, int r_top) {
 // Random access (Appendix A.6): digits r[v * GW_THREADS] (caller passes its own column), directions
 // and binomial product of term index I.
 // With v0 > 0 the walk runs over digits v0 .. D-1 only (I indexes that sub-walk).
+// STRIDE = threads per block of the caller (the digit vectors are stored column-per-thread).
+template <int STRIDE = GW_THREADS>
 __device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsigned char *r, GuanState &st, int v0 = 0) {
     unsigned long long q = I;
     st.dirmask = 0ull;
@@ -108,26 +110,27 @@ __device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsig
         int rv;
         if (q & 1ull) { rv = (int)it.lim[v] - (int)d; st.dirmask |= (1ull << v); }
         else          { rv = (int)d; }
-        r[v * GW_THREADS] = (unsigned char)rv;
+        r[v * STRIDE] = (unsigned char)rv;
         if (it.mult[v] > 1) b *= gw_binom(it.mult[v], rv);
     }
-    st.binom = (it.D - 1 >= v0) ? b * gw_top_weight(it, r[(it.D - 1) * GW_THREADS]) : b;
+    st.binom = (it.D - 1 >= v0) ? b * gw_top_weight(it, r[(it.D - 1) * STRIDE]) : b;
 }
 
 // One Guan step.  Returns the digit that changed; `delta` = +1 / -1.  Must not be called on the
 // last term of the walk.  __ldg-free: everything is in shared memory / registers.
+template <int STRIDE = GW_THREADS>
 __device__ __forceinline__ int guan_step(const GuanItem &it, unsigned char *r, GuanState &st, int &delta, int v0 = 0) {
     int v = v0;
     int cur, nxt, dir;
     for (;;) {
-        cur = r[v * GW_THREADS];
+        cur = r[v * STRIDE];
         dir = ((st.dirmask >> v) & 1ull) ? -1 : 1;
         nxt = cur + dir;
         if (nxt >= 0 && nxt <= (int)it.lim[v]) break;
         st.dirmask ^= (1ull << v);
         ++v;
     }
-    r[v * GW_THREADS] = (unsigned char)nxt;
+    r[v * STRIDE] = (unsigned char)nxt;
     delta = dir;
     const int w = it.mult[v];
     if (w > 1) {

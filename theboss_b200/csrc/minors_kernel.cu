@@ -55,10 +55,10 @@ __device__ __forceinline__ void k3_row_update(unsigned row, double sg, double (&
 }
 
 // dynamic shared memory carve-up (bytes)
-__host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
+__host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C, int threads) {
     size_t x2 = (size_t)rows * W * sizeof(double2);
-    size_t red = (size_t)GW_THREADS * C * sizeof(double2);
-    size_t dig = (size_t)rows * GW_THREADS;
+    size_t red = (size_t)threads * C * sizeof(double2);
+    size_t dig = (size_t)rows * threads;
     return ((x2 > red ? x2 : red) + dig + 15) / 16 * 16 + 16;
 }
 
@@ -68,6 +68,12 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C) {
 // `active` exit at once; the finish kernel applies the same rule.
 #define K3_TERMS_PER_GROUP 192ull
 #define K3_PMAX 512
+// One-warp blocks (THREADS = 32) serve the steps k <= 16, where a sample's whole walk fits one block and the
+// per-block setup (item build, tables, seek: largely single-thread work) dominates: with 4x more, 4x smaller
+// blocks resident per SM the setup of one block overlaps the term loops of the others instead of idling
+// three of its own four warps.
+#define K3_WARP_THREADS 32
+#define K3_WARP_PMAX 128
 struct __align__(16) K3Step { double blow; int off; int pad; };
 __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, unsigned long long per_block) {
     unsigned long long a = (terms + per_block - 1) / per_block;
@@ -76,21 +82,25 @@ __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int ch
     return (int)a;
 }
 
-template <int LPG, int C>
+template <int LPG, int C, int THREADS>
 struct K3Cfg {
-    static constexpr int MINB = (C <= 5) ? 4 : (C <= 8) ? 3 : 2;
+    // same register budget per thread for both block sizes
+    static constexpr int MINB_128 = (C <= 5) ? 4 : (C <= 8) ? 3 : 2;
+    static constexpr int MINB = (MINB_128 * GW_THREADS / THREADS) < 1 ? 1 : (MINB_128 * GW_THREADS / THREADS);
+    static constexpr int PMAX = (THREADS >= GW_THREADS) ? K3_PMAX : K3_WARP_PMAX;
 };
 
 // grid = (chunks, samples).  occ_s / occ_t: [samples][m] uint8 occupations (current input with the
 // newly added particle; outputs sampled so far).  active: NULL or [samples] (0 = skip sample).
 // partials: [samples][chunks][LPG*C][4] double-double partial sums.
-template <int LPG, int C>
-__global__ void __launch_bounds__(GW_THREADS, K3Cfg<LPG, C>::MINB)
+template <int LPG, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS, K3Cfg<LPG, C, THREADS>::MINB)
 k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const unsigned char *__restrict__ occ_s,
                  const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, int step,
                  double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
     constexpr int W = LPG * C;
-    constexpr int GROUPS = GW_THREADS / LPG;
+    constexpr int GROUPS = THREADS / LPG;
+    constexpr int PMAX = K3Cfg<LPG, C, THREADS>::PMAX;
     extern __shared__ __align__(16) unsigned char k3_smem[];
     __shared__ GuanItem item;
     __shared__ short col_mode[W];
@@ -105,7 +115,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     // step tables of the low digits, indexed by the DESTINATION position p inside a period: binomial product of the
     // low digits at p plus the transition that leads there (row byte offset of the changed digit, bit 0 = digit went
     // up); fwd: from p - 1, bwd: from p + 1 (reflected periods).  One 16-byte load per row step.
-    __shared__ K3Step fwd[K3_PMAX], bwd[K3_PMAX];
+    __shared__ K3Step fwd[PMAX], bwd[PMAX];
     __shared__ int low_digits;                 // digits 1 .. low_digits are driven by the table
     __shared__ unsigned period;                // P = prod_{v=1..low_digits} (lim_v + 1): rows per table period
     if (threadIdx.x == 0) {
@@ -113,7 +123,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         if (item.D > 0)
             for (int r = 0; r <= (int)item.lim[0]; ++r)
                 bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
-    } else if (threadIdx.x == 32) {   // a second warp expands the input columns meanwhile
+    } else if (threadIdx.x == (THREADS > 32 ? 32 : 1)) {   // a second warp (lane, in one-warp blocks) expands the input columns meanwhile
         int c = 0;
         for (int v = 0; v < m; ++v)
             for (int a = 0; a < s[v] && c < W; ++a) col_mode[c++] = (short)v;
@@ -125,10 +135,10 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     if (chunk == 0 && threadIdx.x == 0) terms_out[sample] = item.terms;
     if (chunk >= active) return;
     double2 *X2 = reinterpret_cast<double2 *>(k3_smem);
-    size_t x2_bytes = (size_t)D * W * sizeof(double2), red_bytes = (size_t)GW_THREADS * C * sizeof(double2);
+    size_t x2_bytes = (size_t)D * W * sizeof(double2), red_bytes = (size_t)THREADS * C * sizeof(double2);
     unsigned char *rdig = k3_smem + ((x2_bytes > red_bytes ? x2_bytes : red_bytes) + 15) / 16 * 16;
     const double2 *U2 = reinterpret_cast<const double2 *>(U);
-    for (int e = threadIdx.x; e < D * W; e += GW_THREADS) {
+    for (int e = threadIdx.x; e < D * W; e += THREADS) {
         const int v = e / W, c = e - v * W;
         const int cm = col_mode[c];
         double2 x = make_double2(0.0, 0.0);
@@ -149,7 +159,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         int a = 0;
         for (int v = 1; v < D; ++v) {
             const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
-            if (nxt * 16 > raw || nxt > K3_PMAX) break;
+            if (nxt * 16 > raw || nxt > (unsigned long long)PMAX) break;
             P = nxt; a = v;
         }
         period = (unsigned)P;
@@ -158,7 +168,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     __syncthreads();
     const unsigned P = period;
     const int a_low = low_digits;
-    for (unsigned p = threadIdx.x; p < P; p += GW_THREADS) {
+    for (unsigned p = threadIdx.x; p < P; p += THREADS) {
         // digits of position p and p - 1 of the reflected code over digits 1 .. a_low
         double bprod = 1.0;
         unsigned q = p, qm = p ? p - 1 : 0;
@@ -210,7 +220,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         st.dirmask = 0ull; st.binom = 0.0;
         const bool mine = my_periods > 0;
         const unsigned long long hi0 = row_start / P;       // row_start is a multiple of P
-        if (mine) guan_seek(item, hi0, r, st, /*v0=*/a_low + 1);      // digits above the table
+        if (mine) guan_seek<THREADS>(item, hi0, r, st, /*v0=*/a_low + 1);      // digits above the table
         int pos = (hi0 & 1ull) ? (int)P - 1 : 0;            // position inside the period (reflected)
         int pdir = (hi0 & 1ull) ? -1 : 1;
         unsigned off = 0;                                    // rows done in the current period
@@ -230,7 +240,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
                     const unsigned R = (unsigned)item.lim[v] + 1u;
                     const unsigned d = q % R; q /= R;
                     rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
-                } else rv = (int)r[v * GW_THREADS];
+                } else rv = (int)r[v * THREADS];
                 if (v > 0) par += rv;
                 const double coef = 0.5 * (double)((int)item.mult[v] - 2 * rv);
                 const double2 *row = X2 + v * W + col0;
@@ -275,7 +285,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
                 } else {
                     // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
                     int delta;
-                    const int v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+                    const int v = guan_step<THREADS>(item, r, st, delta, /*v0=*/a_low + 1);
                     off_next = v * (W * (int)sizeof(double2)) | (delta > 0 ? 1 : 0);
                     off = 0;
                     pdir = -pdir;
@@ -370,9 +380,10 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     __syncthreads();
     // PARTS threads per column: each adds a contiguous slice of the groups (double-double, group order), thread 0 of
     // the column then adds the PARTS partial sums in slice order -- a fixed summation order, GROUPS / PARTS deep
-    constexpr int PARTS = (GW_THREADS / W) < 1 ? 1 : ((GW_THREADS / W) > 8 ? 8 : (GW_THREADS / W));
+    static_assert(THREADS >= W, "one reduction thread per column");
+    constexpr int PARTS = (THREADS / W) > 8 ? 8 : (THREADS / W);
     constexpr int SLICE = (GROUPS + PARTS - 1) / PARTS;
-    __shared__ double part_sum[GW_THREADS * 4];
+    __shared__ double part_sum[THREADS * 4];
     {
         const int c = threadIdx.x / PARTS, part = threadIdx.x % PARTS;
         if (c < W) {
@@ -546,16 +557,26 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *, unsigned long long);
 
-struct K3Variant { k3_fn fn; int lpg, c; };
+struct K3Variant { k3_fn fn; int lpg, c, threads; };
 #define K3_MAX_C 12
-static K3Variant g_k3[4][K3_MAX_C + 1];   // [log2 LPG][C]
+#define K3_WARP_MAX_C 8
+#define K3_WARP_DEFAULT_MAX_K 16
+static K3Variant g_k3[4][K3_MAX_C + 1];        // [log2 LPG][C], 128-thread blocks
+static K3Variant g_k3w[2][K3_WARP_MAX_C + 1];  // [log2 LPG][C], one-warp blocks (LPG <= 2: k <= 16)
 static bool g_k3_init = false;
 
 template <int LPG, int C>
 static void k3_reg(int lg) {
-    g_k3[lg][C].fn = k3_minors_kernel<LPG, C>;
+    g_k3[lg][C].fn = k3_minors_kernel<LPG, C, GW_THREADS>;
     g_k3[lg][C].lpg = LPG;
     g_k3[lg][C].c = C;
+    g_k3[lg][C].threads = GW_THREADS;
+    if constexpr (LPG <= 2 && C <= K3_WARP_MAX_C) {
+        g_k3w[lg][C].fn = k3_minors_kernel<LPG, C, K3_WARP_THREADS>;
+        g_k3w[lg][C].lpg = LPG;
+        g_k3w[lg][C].c = C;
+        g_k3w[lg][C].threads = K3_WARP_THREADS;
+    }
 }
 template <int LPG>
 static void k3_reg_all(int lg) {
@@ -568,16 +589,20 @@ static void k3_reg_all(int lg) {
 // group.  max_c is 8, except k = 21 .. 24 where two lanes with up to 12 columns measured 4 % faster than four
 // lanes with 6 (no butterfly multiplies; 2 warps/SMSP).  BP_K3_MAX_C overrides the limit for all k (tuning).
 #define K3_DEFAULT_MAX_C 8
+// Steps k <= K3_WARP_DEFAULT_MAX_K run in one-warp blocks (BP_K3_WARP_MAX_K overrides; 0 = never).
 static K3Variant k3_pick(int k) {
-    static int forced_max_c = 0;
+    static int forced_max_c = 0, warp_max_k = K3_WARP_DEFAULT_MAX_K, wide_min_k = 17;
     if (!g_k3_init) {
         k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3);
         const char *e = getenv("BP_K3_MAX_C");
         forced_max_c = e ? atoi(e) : 0;
         if (forced_max_c > K3_MAX_C) forced_max_c = K3_MAX_C;
+        if ((e = getenv("BP_K3_WARP_MAX_K"))) warp_max_k = atoi(e);
+        if (warp_max_k > 2 * K3_WARP_MAX_C) warp_max_k = 2 * K3_WARP_MAX_C;
+        if ((e = getenv("BP_K3_WIDE_MIN_K"))) wide_min_k = atoi(e);   // tuning: first k served by two lanes x up to 12 columns
         g_k3_init = true;
     }
-    int max_c = (k >= 21 && k <= 24) ? K3_MAX_C : K3_DEFAULT_MAX_C;
+    int max_c = (k >= wide_min_k && k <= 24) ? K3_MAX_C : K3_DEFAULT_MAX_C;
     if (forced_max_c >= 7) max_c = forced_max_c;
     int best_lg = -1, best_c = 0, best_w = 1 << 30;
     for (int lg = 0; lg < 4; ++lg) {
@@ -586,8 +611,10 @@ static K3Variant k3_pick(int k) {
         if (c > max_c) continue;
         if (lpg * c < best_w) { best_w = lpg * c; best_lg = lg; best_c = c; }
     }
-    K3Variant none = {nullptr, 0, 0};
-    return best_lg < 0 ? none : g_k3[best_lg][best_c];
+    K3Variant none = {nullptr, 0, 0, 0};
+    if (best_lg < 0) return none;
+    if (k <= warp_max_k && best_lg <= 1 && best_c <= K3_WARP_MAX_C) return g_k3w[best_lg][best_c];
+    return g_k3[best_lg][best_c];
 }
 
 int bp_k3_width(int k) { K3Variant v = k3_pick(k); return v.fn ? v.lpg * v.c : 0; }
@@ -604,8 +631,9 @@ static void k3_plan(bp_context *h, int k, long long samples, int *chunks_out, un
     if (env_tpg < 0) { const char *e = getenv("BP_K3_TPG"); env_tpg = e ? atoi(e) : 0; }
     if (env_cap < 0) { const char *e = getenv("BP_K3_CAP"); env_cap = e ? atoi(e) : 0; }
     K3Variant v = k3_pick(k);
-    const int groups = GW_THREADS / (v.lpg ? v.lpg : 1);
-    const long long fill_blocks = (long long)h->sm_count * 8;
+    const int threads = v.threads ? v.threads : GW_THREADS;
+    const int groups = threads / (v.lpg ? v.lpg : 1);
+    const long long fill_blocks = (long long)h->sm_count * 8 * (GW_THREADS / threads);   // ~32 warps per SM
     long long tpg = (long long)K3_TERMS_PER_GROUP;
     if (samples >= fill_blocks) tpg = 2048;
     else if (2048 * samples / fill_blocks > tpg) tpg = 2048 * samples / fill_blocks;
@@ -649,13 +677,13 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
     if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= %d, got %d", 8 * K3_DEFAULT_MAX_C, k);
     if (k - 1 > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k - 1 <= %d, got k = %d", BP_MAX_N, k);
     if (samples > 65535) return bp_fail(h, BP_ERR_INVALID, "bp_k3_launch: at most 65535 samples per launch");
-    const size_t smem = k3_smem_bytes(k - 1, v.lpg * v.c, v.c);
+    const size_t smem = k3_smem_bytes(k - 1, v.lpg * v.c, v.c, v.threads);
     if (smem > 24 * 1024) {   // static shared memory (step tables) takes ~17 KB of the 48 KB that need no opt-in
         cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)chunks, (unsigned)samples);
-    v.fn<<<grid, GW_THREADS, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms,
+    v.fn<<<grid, v.threads, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms,
                                                 bp_k3_per_block(h, k, samples));
     BP_CHECK_LAUNCH(h);
     return BP_OK;
