@@ -14,12 +14,15 @@ struct K3Finish {
     const double *tape; int tape_stride;                       // [samples][1 + 2n]
     unsigned char *remaining; int *n_remaining; int n;         // [samples][n], [samples]
     const int *steps_total;                                    // [samples]
+    // launch slot -> sample (NULL: identity).  Runs whose samples stop after different numbers of steps launch only
+    // the samples still active; partials are indexed by launch slot, every per-sample array by sample.
+    const int *order;
 };
 
 int bp_k3_width(int k);
 int bp_k3_chunks(bp_context *h, int k, long long samples);
 unsigned long long bp_k3_per_block(bp_context *h, int k, long long samples);
 int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const unsigned char *d_s, const unsigned char *d_t,
-                 const int *d_steps_total, int k, long long samples, int chunks, double *d_partials,
+                 const int *d_steps_total, const int *d_order, int k, long long samples, int chunks, double *d_partials,
                  unsigned long long *d_terms);
 int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples);

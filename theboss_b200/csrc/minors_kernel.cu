@@ -90,14 +90,14 @@ struct K3Cfg {
     static constexpr int PMAX = (THREADS >= GW_THREADS) ? K3_PMAX : K3_WARP_PMAX;
 };
 
-// grid = (chunks, samples).  occ_s / occ_t: [samples][m] uint8 occupations (current input with the
-// newly added particle; outputs sampled so far).  active: NULL or [samples] (0 = skip sample).
-// partials: [samples][chunks][LPG*C][4] double-double partial sums.
+// grid = (chunks, launch slots).  order: NULL (slot = sample) or [slots] sample of every launch slot.
+// occ_s / occ_t: [samples][m] uint8 occupations (current input with the newly added particle; outputs
+// sampled so far).  partials: [slots][chunks][LPG*C][4] double-double partial sums.
 template <int LPG, int C, int THREADS>
 __global__ void __launch_bounds__(THREADS, K3Cfg<LPG, C, THREADS>::MINB)
 k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const unsigned char *__restrict__ occ_s,
-                 const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, int step,
-                 double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
+                 const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, const int *__restrict__ order,
+                 int step, double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
     constexpr int W = LPG * C;
     constexpr int GROUPS = THREADS / LPG;
     constexpr int PMAX = K3Cfg<LPG, C, THREADS>::PMAX;
@@ -105,9 +105,10 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     __shared__ GuanItem item;
     __shared__ short col_mode[W];
 
-    const int sample = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int slot = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int sample = order ? order[slot] : slot;
     const double *U = U0 + (size_t)sample * u_stride;   // u_stride = 0: one interferometer for all samples
-    double *my_part = partials + ((size_t)sample * chunks + chunk) * (size_t)(W * 4);
+    double *my_part = partials + ((size_t)slot * chunks + chunk) * (size_t)(W * 4);
     if (steps_total && step >= steps_total[sample]) return;   // uniform-loss variant: this sample is complete
 
     const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
@@ -431,12 +432,13 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
     __shared__ short first_col[BP_MAX_MODES];
     __shared__ double total_sh;
     __shared__ int idx_sh;
-    // chunk reduction of a single sample that had the whole GPU (up to 296 chunk blocks): K3F_PARTS interleaved slices
+    // chunk reduction of the few samples that had the whole GPU (up to 296 chunk blocks each): K3F_PARTS interleaved slices
     // per column summed by different threads, then added in slice order (fixed order); batches (<= 32 chunks) use one slice
     __shared__ short occ_mode[BP_MAX_N + 2], occ_col[BP_MAX_N + 2];
     __shared__ int nocc_sh;
-    extern __shared__ double psum[];   // [(BP_MAX_N + 2) * parts * 4]: parts = K3F_PARTS for a lone sample, else 1 (host sizes it)
-    const int sample = blockIdx.x, m = a.m, k = a.step + 1;
+    extern __shared__ double psum[];   // [(BP_MAX_N + 2) * parts * 4]: parts = K3F_PARTS when chunks > 32, else 1 (host sizes it)
+    const int slot = blockIdx.x, m = a.m, k = a.step + 1;
+    const int sample = a.order ? a.order[slot] : slot;
     if (a.steps_total && a.step >= a.steps_total[sample]) return;
     unsigned char *s = a.occ_s + (size_t)sample * m, *t = a.occ_t + (size_t)sample * m;
     if (threadIdx.x == 0) {
@@ -455,8 +457,8 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
         const double scale = ldexp(1.0, -(k - 1));
         const int nocc = nocc_sh;
         const int active = k3_active_chunks(a.terms[sample], a.chunks, a.per_block);
-        const int parts = (gridDim.x == 1 && active > 32) ? K3F_PARTS : 1;
-        const double *base = a.partials + ((size_t)sample * a.chunks) * (size_t)(a.W * 4);
+        const int parts = (a.chunks > 32 && active > 32) ? K3F_PARTS : 1;   // host: 512 threads and K3F_PARTS slices of psum when chunks > 32
+        const double *base = a.partials + ((size_t)slot * a.chunks) * (size_t)(a.W * 4);
         for (int it = threadIdx.x; it < nocc * parts; it += blockDim.x) {
             const int i = it / parts, p = it - i * parts;
             const double *col = base + 4 * (int)occ_col[i];
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, int, double *, unsigned long long *, unsigned long long);
+typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, const int *, int, double *, unsigned long long *, unsigned long long);
 
 struct K3Variant { k3_fn fn; int lpg, c, threads; };
 #define K3_MAX_C 12
@@ -668,9 +670,10 @@ unsigned long long bp_k3_per_block(bp_context *h, int k, long long samples) {
     return pb;
 }
 
-// Enqueue the minors main kernel for step k (= particles in occ_s) over `samples` samples.
+// Enqueue the minors main kernel for step k (= particles in occ_s) over `samples` launch slots (d_order: slot -> sample,
+// NULL = identity).
 int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const unsigned char *d_s, const unsigned char *d_t,
-                 const int *d_steps_total, int k, long long samples, int chunks, double *d_partials,
+                 const int *d_steps_total, const int *d_order, int k, long long samples, int chunks, double *d_partials,
                  unsigned long long *d_terms) {
     if (k <= 1) return BP_OK;   // handled by the finish kernel
     K3Variant v = k3_pick(k);
@@ -683,16 +686,17 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
         if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     }
     dim3 grid((unsigned)chunks, (unsigned)samples);
-    v.fn<<<grid, v.threads, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, k - 1, d_partials, d_terms,
+    v.fn<<<grid, v.threads, smem, h->stream>>>(dU, u_stride, m, d_s, d_t, d_steps_total, d_order, k - 1, d_partials, d_terms,
                                                 bp_k3_per_block(h, k, samples));
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }
 
 int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples) {
-    // a lone sample may have up to 2 x SM-count chunk partials per column to add: give its block more threads
-    const int threads = samples == 1 ? 512 : K3F_THREADS;
-    const size_t smem = sizeof(double) * 4 * (BP_MAX_N + 2) * (samples == 1 ? K3F_PARTS : 1);
+    // few samples (< 2 x SM count) may have up to 2 x SM-count chunk partials per column to add: give their blocks more threads
+    const bool many_chunks = a.chunks > 32;
+    const int threads = many_chunks ? 512 : K3F_THREADS;
+    const size_t smem = sizeof(double) * 4 * (BP_MAX_N + 2) * (many_chunks ? K3F_PARTS : 1);
     k3_finish_kernel<<<(unsigned)samples, threads, smem, h->stream>>>(a);
     BP_CHECK_LAUNCH(h);
     return BP_OK;

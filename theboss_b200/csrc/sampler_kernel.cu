@@ -142,7 +142,7 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     BP_CUDA(h, cudaMemcpyAsync(d_s, hs, 2 * (size_t)m, cudaMemcpyHostToDevice, h->stream));
     const double *dU = (const double *)h->d_buf[BP_SLOT_AUX];
     double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
-    if ((rc = bp_k3_launch(h, dU, 0, m, d_s, d_t, nullptr, (int)k, 1, chunks, d_part, d_terms))) return rc;
+    if ((rc = bp_k3_launch(h, dU, 0, m, d_s, d_t, nullptr, nullptr, (int)k, 1, chunks, d_part, d_terms))) return rc;
     double *d_min = (double *)h->d_buf[BP_SLOT_OUT], *d_pmf = d_min + 2 * (size_t)m;
     K3Finish a;
     memset(&a, 0, sizeof(a));
@@ -223,11 +223,16 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
         if ((long long)ch * W > (long long)max_chunks * maxW) { max_chunks = ch; maxW = W; }
     }
     const size_t u_count = per_sample ? (size_t)batch : 1;
-    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 16) + u_count * (size_t)m + (size_t)m + 256;
+    // Samples of a run stop after different numbers of steps when particles are lost (eta >= 0: binomial draw on the
+    // device) or when every sample has its own input state: such runs launch only the samples still active at step k
+    // (launch slot -> sample through `order`, samples sorted by their step count, longest first).
+    const bool ragged = per_sample || eta >= 0.0;
+    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 20) + u_count * (size_t)m + (size_t)m + 256;
     if ((rc = bp_reserve(h, BP_SLOT_AUX, ub * u_count + sizeof(double) * (size_t)(n + 2)))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_STATE, state_bytes))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_TAPE, sizeof(double) * (size_t)batch * stride))) return rc;
-    if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)maxW * max_chunks * (size_t)batch))) return rc;
+    if (!ragged && (rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)maxW * max_chunks * (size_t)batch))) return rc;
+    if (ragged && (rc = bp_reserve_pinned(h, sizeof(int) * 2 * (size_t)batch + 64))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(int) * (size_t)batch * m))) return rc;
 
     double *dU = (double *)h->d_buf[BP_SLOT_AUX];
@@ -239,14 +244,15 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
     unsigned long long *d_terms = (unsigned long long *)base;
     int *d_nrem = (int *)(d_terms + batch);
     int *d_steps = d_nrem + batch;
-    unsigned char *d_occ_s = (unsigned char *)(d_steps + batch);
+    int *d_order = d_steps + batch;
+    unsigned char *d_occ_s = (unsigned char *)(d_order + batch);
     unsigned char *d_occ_t = d_occ_s + (size_t)batch * m;
     unsigned char *d_rem = d_occ_t + (size_t)batch * m;
     unsigned char *d_s0 = d_rem + (size_t)batch * n;
     if (!per_sample) BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data(), (size_t)m, cudaMemcpyHostToDevice, h->stream));
     double *d_tape = (double *)h->d_buf[BP_SLOT_TAPE];
-    double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
     int *d_out = (int *)h->d_buf[BP_SLOT_OUT];
+    std::vector<long long> active(n + 2, 0);   // active[k] = samples that take at least k steps
     const size_t u_stride = per_sample ? 2 * (size_t)m * m : 0, s0_stride = per_sample ? (size_t)m : 0;
 
     for (long long done = 0; done < n_samples; done += batch) {
@@ -266,17 +272,47 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
         k4_init_kernel<<<(unsigned)((S + 127) / 128), 128, 0, h->stream>>>(d_s0, s0_stride, m, n, eta >= 0.0 ? d_w : nullptr, d_tape, stride, S,
                                                                           d_occ_s, d_occ_t, d_rem, d_nrem, d_steps);
         BP_CHECK_LAUNCH(h);
+        for (int k = 0; k <= n + 1; ++k) active[k] = (k <= n) ? S : 0;
+        if (ragged) {
+            // step counts back to the host (4 bytes per sample), counting sort by step count (descending, stable)
+            int *h_steps = (int *)h->h_pin, *h_order = h_steps + S;
+            BP_CUDA(h, cudaMemcpyAsync(h_steps, d_steps, sizeof(int) * (size_t)S, cudaMemcpyDeviceToHost, h->stream));
+            BP_CUDA(h, cudaStreamSynchronize(h->stream));
+            std::vector<long long> first(n + 2, 0);
+            for (long long i = 0; i < S; ++i) {
+                const int st = h_steps[i];
+                if (st < 0 || st > n) return bp_fail(h, BP_ERR_CUDA, "%s: sample %lld reports %d steps (n = %d)", who, i, st, n);
+                first[st]++;
+            }
+            long long run = 0;
+            for (int st = n; st >= 0; --st) { const long long c = first[st]; first[st] = run; run += c; active[st] = run; }
+            active[0] = S; active[n + 1] = 0;
+            for (long long i = 0; i < S; ++i) h_order[first[h_steps[i]]++] = (int)i;
+            BP_CUDA(h, cudaMemcpyAsync(d_order, h_order, sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, h->stream));
+            size_t need = 1;
+            for (int k = 2; k <= n; ++k) {
+                if (active[k] == 0) break;
+                const size_t v = (size_t)bp_k3_chunks(h, k, active[k]) * (size_t)bp_k3_width(k) * (size_t)active[k];
+                if (v > need) need = v;
+            }
+            if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * need))) return rc;
+        }
+        double *d_part = (double *)h->d_buf[BP_SLOT_PARTIALS];
         for (int k = 1; k <= n; ++k) {
-            const int chunks = bp_k3_chunks(h, k, S), W = bp_k3_width(k);
-            if ((rc = bp_k3_launch(h, dU, u_stride, m, d_occ_s, d_occ_t, d_steps, k, S, chunks, d_part, d_terms))) return rc;
+            const long long A = active[k];   // samples that reach step k (all of them unless the run is ragged)
+            if (A == 0) break;
+            const int chunks = bp_k3_chunks(h, k, A), W = bp_k3_width(k);
+            if ((rc = bp_k3_launch(h, dU, u_stride, m, d_occ_s, d_occ_t, d_steps, ragged ? d_order : nullptr, k, A, chunks, d_part, d_terms)))
+                return rc;
             K3Finish a;
             memset(&a, 0, sizeof(a));
             a.U = dU; a.u_stride = u_stride; a.m = m; a.W = W; a.chunks = chunks; a.step = k - 1; a.partials = d_part;
-            a.terms = d_terms; a.per_block = bp_k3_per_block(h, k, S);
+            a.terms = d_terms; a.per_block = bp_k3_per_block(h, k, A);
             a.occ_s = d_occ_s; a.occ_t = d_occ_t;
             a.tape = d_tape; a.tape_stride = stride; a.remaining = d_rem; a.n_remaining = d_nrem; a.n = n;
             a.steps_total = d_steps;
-            if ((rc = bp_k3_finish_launch(h, a, S))) return rc;
+            a.order = ragged ? d_order : nullptr;
+            if ((rc = bp_k3_finish_launch(h, a, A))) return rc;
         }
         const long long cnt = S * m;
         k4_output_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(d_occ_t, cnt, d_out);
