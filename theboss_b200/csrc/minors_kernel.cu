@@ -441,17 +441,38 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
     const int sample = a.order ? a.order[slot] : slot;
     if (a.steps_total && a.step >= a.steps_total[sample]) return;
     unsigned char *s = a.occ_s + (size_t)sample * m, *t = a.occ_t + (size_t)sample * m;
-    if (threadIdx.x == 0) {
-        int c = 0, nocc = 0;
-        for (int v = 0; v < m; ++v) {
-            first_col[v] = s[v] ? (short)c : (short)-1;
-            if (s[v] && nocc < BP_MAX_N + 2) { occ_mode[nocc] = (short)v; occ_col[nocc] = (short)c; ++nocc; }
-            c += s[v];
-        }
-        nocc_sh = nocc;
-        idx_sh = 0;
+    __shared__ unsigned char s_sh[BP_MAX_MODES];               // input occupation of this sample
+    __shared__ double sp_re[BP_MAX_N + 2], sp_im[BP_MAX_N + 2];  // s_i * P_i of the occupied input modes, mode order
+    for (int v = threadIdx.x; v < m; v += blockDim.x) {
+        const unsigned char sv = s[v];
+        s_sh[v] = sv;
+        P[v] = make_double2(k == 1 ? (double)sv : 0.0, 0.0);
     }
-    for (int v = threadIdx.x; v < m; v += blockDim.x) P[v] = make_double2(k == 1 ? (double)s[v] : 0.0, 0.0);
+    if (threadIdx.x == 0) idx_sh = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // first column of every occupied input mode and the list of occupied modes: warp scan over 32 modes at a time
+        // (low half: particles = columns before the mode, high half: occupied modes before it)
+        const int lane = threadIdx.x;
+        int carry_c = 0, carry_o = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int v = base + lane;
+            const int sv = v < m ? (int)s_sh[v] : 0, occ = sv > 0 ? 1 : 0;
+            int x = sv | (occ << 16);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            const int c = carry_c + (x & 0xffff) - sv, o = carry_o + (x >> 16) - occ;
+            if (v < m) first_col[v] = occ ? (short)c : (short)-1;
+            if (occ && o < BP_MAX_N + 2) { occ_mode[o] = (short)v; occ_col[o] = (short)c; }
+            const int tot = __shfl_sync(0xffffffffu, x, 31);
+            carry_c += tot & 0xffff;
+            carry_o += tot >> 16;
+        }
+        if (lane == 0) nocc_sh = carry_o < BP_MAX_N + 2 ? carry_o : BP_MAX_N + 2;
+    }
     __syncthreads();
     if (k > 1) {
         const double scale = ldexp(1.0, -(k - 1));
@@ -481,24 +502,46 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
                 re = dd_add(re, x);
                 im = dd_add(im, y);
             }
-            P[occ_mode[i]] = make_double2((re.hi + re.lo) * scale, (im.hi + im.lo) * scale);
+            const int mode = occ_mode[i];
+            const double2 val = make_double2((re.hi + re.lo) * scale, (im.hi + im.lo) * scale);
+            P[mode] = val;
+            const double cnt = (double)s_sh[mode];               // permanent_added = s_i * P_i
+            sp_re[i] = cnt * val.x; sp_im[i] = cnt * val.y;
         }
-        __syncthreads();
+    } else {
+        for (int i = threadIdx.x; i < nocc_sh; i += blockDim.x) {   // k = 1: P_i = s_i
+            const double cnt = (double)s_sh[occ_mode[i]];
+            sp_re[i] = cnt * cnt; sp_im[i] = cnt * 0.0;
+        }
     }
+    __syncthreads();
     if (a.minors_out)
         for (int v = threadIdx.x; v < m; v += blockDim.x) {
             a.minors_out[2 * ((size_t)sample * m + v)] = P[v].x; a.minors_out[2 * ((size_t)sample * m + v) + 1] = P[v].y;
         }
     if (!a.pmf_out && !a.tape) return;
     const double2 *U2 = reinterpret_cast<const double2 *>(a.U + (size_t)sample * a.u_stride);
+    const int nocc_all = nocc_sh;
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         double re = 0.0, im = 0.0;
-        for (int i = 0; i < m; ++i) {
-            if (first_col[i] < 0) continue;
-            // permanent_added = s_i * P_i; permanent_added *= U[j][i]; permanent += permanent_added
-            const double cnt = (double)s[i];
-            const double sr = cnt * P[i].x, si = cnt * P[i].y;
-            const double2 u = U2[j * m + i];
+        const double2 *Uj = U2 + (size_t)j * m;
+        // permanent_added = s_i * P_i; permanent_added *= U[j][i]; permanent += permanent_added -- occupied modes i in
+        // ascending order (the reference skips nothing but adds exact zeros for the others); four loads in flight
+        int i = 0;
+        for (; i + 4 <= nocc_all; i += 4) {
+            double2 u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[q] = Uj[occ_mode[i + q]];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double sr = sp_re[i + q], si = sp_im[i + q];
+                re += __dsub_rn(__dmul_rn(sr, u[q].x), __dmul_rn(si, u[q].y));
+                im += __dadd_rn(__dmul_rn(sr, u[q].y), __dmul_rn(si, u[q].x));
+            }
+        }
+        for (; i < nocc_all; ++i) {
+            const double sr = sp_re[i], si = sp_im[i];
+            const double2 u = Uj[occ_mode[i]];
             re += __dsub_rn(__dmul_rn(sr, u.x), __dmul_rn(si, u.y));
             im += __dadd_rn(__dmul_rn(sr, u.y), __dmul_rn(si, u.x));
         }
