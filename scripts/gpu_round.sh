@@ -19,4 +19,11 @@ tail -2 gpurun_out/ncu_k3.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k2_perm_kernel -s 1 -c 1 -f -o gpurun_out/k2_c2 python scripts/profile_k2.py 10000 > gpurun_out/ncu_k2.log 2>&1
 tail -2 gpurun_out/ncu_k2.log
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/k3_launches.csv python scripts/profile_k3.py 24 4096 0 > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size --clock-control none -k regex:k3_minors --csv --log-file gpurun_out/k3_steps_n24.csv python scripts/profile_k3.py 24 4096 0 > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size --clock-control none -k regex:k3_minors --csv --log-file gpurun_out/k3_steps_n20.csv python scripts/profile_k3.py 20 16384 0 > /dev/null 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum,launch__grid_size,launch__block_size --clock-control none --csv --log-file gpurun_out/c5i_launches.csv python scripts/profile_c5i.py 4096 0 > /dev/null 2>&1
 bash scripts/time_sampling.sh
+timeout 100 python scripts/profile_c5i.py 4096 3 | tee -a gpurun_out/time_sampling.txt
+timeout 100 python scripts/ab_k3.py 3 | tee -a gpurun_out/time_sampling.txt
+timeout 100 python scripts/time_c1.py | tee -a gpurun_out/time_sampling.txt
+timeout 100 python scripts/c3_latency.py | tee -a gpurun_out/time_sampling.txt

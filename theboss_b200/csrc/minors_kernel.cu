@@ -608,7 +608,6 @@ struct K3Variant { k3_fn fn; int lpg, c, threads; };
 #define K3_WARP_DEFAULT_MAX_K 16
 static K3Variant g_k3[4][K3_MAX_C + 1];        // [log2 LPG][C], 128-thread blocks
 static K3Variant g_k3w[2][K3_WARP_MAX_C + 1];  // [log2 LPG][C], one-warp blocks (LPG <= 2: k <= 16)
-static bool g_k3_init = false;
 
 template <int LPG, int C>
 static void k3_reg(int lg) {
@@ -631,22 +630,25 @@ static void k3_reg_all(int lg) {
 }
 
 // Variant for k input columns: smallest padded width LPG * C >= k with C <= max_c, preferring fewer lanes per
-// group.  max_c is 8, except k = 21 .. 24 where two lanes with up to 12 columns measured 4 % faster than four
-// lanes with 6 (no butterfly multiplies; 2 warps/SMSP).  BP_K3_MAX_C overrides the limit for all k (tuning).
+// group.  max_c is 8, except k = 17 .. 24 where two lanes with up to 12 columns beat four lanes with up to 6 (no
+// butterfly multiplies; 2 warps/SMSP): 4 % at k = 21 .. 24, 7 % on a whole n = 20 run for k = 17 .. 20
+// (profiles/r01_k3_block_shapes.txt).  Steps k <= K3_WARP_DEFAULT_MAX_K run in one-warp blocks.
+// Tuning knobs, read once: BP_K3_MAX_C (column limit for all k), BP_K3_WIDE_MIN_K (first k of the two-lane rule),
+// BP_K3_WARP_MAX_K (0 = never one-warp blocks).
 #define K3_DEFAULT_MAX_C 8
-// Steps k <= K3_WARP_DEFAULT_MAX_K run in one-warp blocks (BP_K3_WARP_MAX_K overrides; 0 = never).
 static K3Variant k3_pick(int k) {
     static int forced_max_c = 0, warp_max_k = K3_WARP_DEFAULT_MAX_K, wide_min_k = 17;
-    if (!g_k3_init) {
+    static const bool ready = [] {   // thread-safe one-time registration (C++11 static initialisation)
         k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3);
         const char *e = getenv("BP_K3_MAX_C");
         forced_max_c = e ? atoi(e) : 0;
         if (forced_max_c > K3_MAX_C) forced_max_c = K3_MAX_C;
         if ((e = getenv("BP_K3_WARP_MAX_K"))) warp_max_k = atoi(e);
         if (warp_max_k > 2 * K3_WARP_MAX_C) warp_max_k = 2 * K3_WARP_MAX_C;
-        if ((e = getenv("BP_K3_WIDE_MIN_K"))) wide_min_k = atoi(e);   // tuning: first k served by two lanes x up to 12 columns
-        g_k3_init = true;
-    }
+        if ((e = getenv("BP_K3_WIDE_MIN_K"))) wide_min_k = atoi(e);
+        return true;
+    }();
+    (void)ready;
     int max_c = (k >= wide_min_k && k <= 24) ? K3_MAX_C : K3_DEFAULT_MAX_C;
     if (forced_max_c >= 7) max_c = forced_max_c;
     int best_lg = -1, best_c = 0, best_w = 1 << 30;

@@ -34,6 +34,7 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
         self._weights: Dict[int, np.ndarray] = {}
         self._norms: Dict[int, np.ndarray] = {}
         self._prefetched: Dict[Tuple[int, ...], np.ndarray] = {}
+        self._draw_cache: Dict[Tuple[int, ...], Tuple[List[float], float]] = {}
 
     def set_new_matrix(self, new_matrix) -> None:
         self._bs_permanent_calculator.matrix = new_matrix
@@ -135,6 +136,7 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
         self.number_of_input_photons = int(sum(input_state))
         self._prepare_substates()
         self.pmfs = {}
+        self._draw_cache = {}
         samples = []
         while len(samples) < samples_number:
             self._fill_r_sample()
@@ -143,9 +145,19 @@ class GeneralizedCliffordsSimulationStrategy(SimulationStrategyInterface):
 
     def _fill_r_sample(self) -> None:
         self.r_sample = [0 for _ in self.input_state]
-        while self.number_of_input_photons > sum(self.r_sample):
-            pmf, _ = self._pmf_for(tuple(self.r_sample))
-            threshold = np.random.random() * sum(pmf)   # pmfs are not normalised (:253-255)
+        n_left = self.number_of_input_photons
+        while n_left > 0:
+            key = tuple(self.r_sample)
+            cached = self._draw_cache.get(key)
+            if cached is None:
+                # the memoised layer as Python floats plus its left-to-right sum: the same numbers and the same
+                # summation order as sum(pmf) / the running sum over the ndarray (:253-262), without re-boxing
+                # every element at every visit
+                pmf_list = self._pmf_for(key)[0].tolist()
+                cached = self._draw_cache[key] = (pmf_list, sum(pmf_list))
+            pmf, total = cached
+            n_left -= 1
+            threshold = np.random.random() * total      # pmfs are not normalised (:253-255)
             running, index = 0, 0
             for p in pmf:
                 running += p
