@@ -114,6 +114,7 @@ int bp_destroy(bp_handle h) {
     for (int i = 0; i < 8; ++i)
         if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->d_counter) cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->stream);

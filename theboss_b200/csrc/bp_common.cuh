@@ -23,6 +23,7 @@ struct bp_context {
     void *h_pin = nullptr;
     size_t h_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned int *d_counter = nullptr;   // K1: block arrival counter of the fused finish (always zero between launches)
     char err[512] = {0};
 };
 

@@ -9,12 +9,16 @@
 //     starts on a multiple of 2^6, so that inside a 64-step window all lanes of a warp flip the
 //     same row (ctz of the low bits) and the shared-memory row read is a broadcast;
 //   * the N running column sums live in registers (static indexing: N is a template
-//     parameter), the pre-doubled matrix 2A lives in shared memory;
-//   * per step: N complex (sum += +-2A[row]) updates and an (N-1)-multiply complex product in
+//     parameter), the matrix A lives in shared memory.  The sums are kept HALVED (s/2, flips add
+//     +-A[row] instead of +-2A[row]): no pre-doubling pass over the matrix; every product is then
+//     exactly 2^-N times the reference's (powers of two: no rounding), undone when the partials
+//     are combined;
+//   * per step: N complex (sum += +-A[row]) updates and an (N-1)-multiply complex product in
 //     three independent chains for ILP; (6N-2) FP64 issue slots for (8N-4) useful flops;
 //   * terms are added in plain FP64 inside a 64-step window, windows are folded into a
 //     double-double accumulator per thread, then warp-shuffle + shared-memory block reduction in
-//     double-double; one partial per block, summed in block order by glynn_finish_kernel.
+//     double-double; one partial per block, summed in block order (and scaled by 2^N) by the last
+//     block to finish when one kernel covers the whole range, else by glynn_finish_kernel.
 //
 // Two kernels share this layout:
 //   glynn_gray_kernel<N>    generic: any step range, one Gray step per loop iteration.
@@ -59,17 +63,59 @@ __device__ __forceinline__ void k1_product(const double (&sr)[N], const double (
     pi = p[0].im;
 }
 
+// Sums `nblocks` double-double complex partials in block order and scales by 2^scale_log2 (exact).  One warp.
+__device__ __forceinline__ void k1_sum_partials(const double *partials, int nblocks, int scale_log2, double *out_dd) {
+    const int lane = threadIdx.x & 31;
+    dd re = {0.0, 0.0}, im = {0.0, 0.0};
+    for (int b = lane; b < nblocks; b += 32) {
+        dd a = {__ldcg(partials + 4 * b + 0), __ldcg(partials + 4 * b + 1)}, c = {__ldcg(partials + 4 * b + 2), __ldcg(partials + 4 * b + 3)};
+        re = dd_add(re, a);
+        im = dd_add(im, c);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        re = dd_add(re, dd_shfl_down(re, d));
+        im = dd_add(im, dd_shfl_down(im, d));
+    }
+    if (lane == 0) {
+        out_dd[0] = ldexp(re.hi, scale_log2); out_dd[1] = ldexp(re.lo, scale_log2);
+        out_dd[2] = ldexp(im.hi, scale_log2); out_dd[3] = ldexp(im.lo, scale_log2);
+    }
+}
+
+// Block epilogue shared by both kernels: thread 0 holds the block's partial.  With a counter (one kernel covers the whole
+// range) the last block to arrive adds all partials in block order -- the same order and arithmetic as glynn_finish_kernel,
+// so the result does not depend on which block is last -- and resets the counter for the next launch.
+__device__ __forceinline__ void k1_block_epilogue(dd acc_re, dd acc_im, double *__restrict__ partials, unsigned int *counter,
+                                                  int scale_log2, double *__restrict__ out_dd) {
+    __shared__ int is_last;
+    if (threadIdx.x == 0) {
+        double *o = partials + 4 * (size_t)blockIdx.x;
+        o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo;
+        int last = 0;
+        if (counter) {
+            __threadfence();
+            last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        is_last = last;
+    }
+    if (!counter) return;
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        k1_sum_partials(partials, (int)gridDim.x, scale_log2, out_dd);
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
 template <int N>
 __global__ void __launch_bounds__(K1_THREADS, K1Cfg<N>::MINB)
 glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
-                  double *__restrict__ partials) {
-    __shared__ double2 sA2[N * N];                    // 2*A, row-major
+                  double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd) {
+    __shared__ double2 sA2[N * N];                    // A, row-major (the column sums are kept halved)
     __shared__ double red[4 * (K1_THREADS / 32)];
 
-    for (int e = threadIdx.x; e < N * N; e += K1_THREADS) {
-        double2 v = reinterpret_cast<const double2 *>(A)[e];
-        sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
-    }
+    for (int e = threadIdx.x; e < N * N; e += K1_THREADS) sA2[e] = reinterpret_cast<const double2 *>(A)[e];
     __syncthreads();
 
     const uint64_t gtid = (uint64_t)blockIdx.x * K1_THREADS + threadIdx.x;
@@ -86,7 +132,7 @@ glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64
         const uint64_t g0 = start ^ (start >> 1);
 #pragma unroll 1
         for (int i = 0; i < N; ++i) {
-            const double sg = ((g0 >> i) & 1ull) ? -0.5 : 0.5;   // times the pre-doubled entry
+            const double sg = ((g0 >> i) & 1ull) ? -0.5 : 0.5;   // halved sums
             const double2 *row = sA2 + i * N;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
@@ -128,10 +174,7 @@ glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64
     }
 
     block_reduce_dd(acc_re, acc_im, red);
-    if (threadIdx.x == 0) {
-        double *o = partials + 4 * (size_t)blockIdx.x;
-        o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo;
-    }
+    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd);
 }
 
 
@@ -150,7 +193,7 @@ struct K1BCfg {
     static constexpr int NCH = (N <= 30) ? 1 : 2;
 };
 
-__constant__ double2 c_A2[BP_MAX_N * BP_MAX_N];   // 2*A of the permanent in flight (row stride N)
+__constant__ double2 c_A2[BP_MAX_N * BP_MAX_N];   // A of the permanent in flight (row stride N)
 
 // product of the N column sums in NCH (1 or 2) chains; the final multiplication is fused into the window
 // accumulator (PLUS: w += p, else w -= p): 4(N-2) + 4 FP64 instructions per step
@@ -188,14 +231,11 @@ __device__ __forceinline__ void k1b_flip_const(double (&sr)[N], double (&si)[N],
 template <int N>
 __global__ void __launch_bounds__(K1BCfg<N>::THREADS, 1)
 glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
-                    double *__restrict__ partials) {
+                    double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd) {
     constexpr int THREADS = K1BCfg<N>::THREADS;
     __shared__ double2 sA2[N * N];
     __shared__ double red[4 * (THREADS / 32)];
-    for (int e = threadIdx.x; e < N * N; e += THREADS) {
-        double2 v = reinterpret_cast<const double2 *>(A)[e];
-        sA2[e] = make_double2(2.0 * v.x, 2.0 * v.y);
-    }
+    for (int e = threadIdx.x; e < N * N; e += THREADS) sA2[e] = reinterpret_cast<const double2 *>(A)[e];
     __syncthreads();
     const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
     const uint64_t start = lo + gtid * span;
@@ -251,40 +291,19 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
         acc_im = dd_add_d(acc_im, wi);
     }
     block_reduce_dd(acc_re, acc_im, red);
-    if (threadIdx.x == 0) {
-        double *o = partials + 4 * (size_t)blockIdx.x;
-        o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo;
-    }
+    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd);
 }
 
-__global__ void k1b_double_kernel(const double *__restrict__ A, int count, double *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = 2.0 * A[i];
-}
-
-// Sums `nblocks` double-double complex partials in block order.  One warp.
-__global__ void glynn_finish_kernel(const double *__restrict__ partials, int nblocks,
+// Sums the partials of several kernels (bulk + unaligned head / tail) in block order; one warp.
+__global__ void glynn_finish_kernel(const double *__restrict__ partials, int nblocks, int scale_log2,
                                     double *__restrict__ out_dd) {
-    dd re = {0.0, 0.0}, im = {0.0, 0.0};
-    for (int b = threadIdx.x; b < nblocks; b += 32) {
-        dd a = {partials[4 * b + 0], partials[4 * b + 1]}, c = {partials[4 * b + 2], partials[4 * b + 3]};
-        re = dd_add(re, a);
-        im = dd_add(im, c);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        re = dd_add(re, dd_shfl_down(re, d));
-        im = dd_add(im, dd_shfl_down(im, d));
-    }
-    if (threadIdx.x == 0) {
-        out_dd[0] = re.hi; out_dd[1] = re.lo; out_dd[2] = im.hi; out_dd[3] = im.lo;
-    }
+    k1_sum_partials(partials, nblocks, scale_log2, out_dd);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host-side launch
 // ---------------------------------------------------------------------------------------------
-typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *);
+typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *, unsigned int *, double *);
 
 static k1_fn g_k1_fn[BP_MAX_N + 1], g_k1_bulk[BP_MAX_N + 1];
 static int g_k1_minb[BP_MAX_N + 1], g_k1_bulk_threads[BP_MAX_N + 1];
@@ -304,7 +323,8 @@ static std::mutex g_const_mutex;
 static cudaEvent_t g_const_event[64];
 static bool g_const_event_valid[64];
 
-static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_partials, int *grid_out) {
+static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_partials, int *grid_out,
+                      unsigned int *d_counter, double *d_out_dd) {
     const uint64_t window = 1ull << K1_WINDOW_LOG2;
     const uint64_t total = hi - lo;
     const uint64_t max_threads = (uint64_t)h->sm_count * g_k1_minb[N] * K1_THREADS;
@@ -314,7 +334,7 @@ static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint6
     uint64_t nthreads = (total + span - 1) / span;
     if (nthreads == 0) nthreads = 1;
     const int grid = (int)((nthreads + K1_THREADS - 1) / K1_THREADS);
-    g_k1_fn[N]<<<grid, K1_THREADS, 0, h->stream>>>(dA, lo, hi, span, d_partials);
+    g_k1_fn[N]<<<grid, K1_THREADS, 0, h->stream>>>(dA, lo, hi, span, d_partials, d_counter, d_out_dd);
     BP_CHECK_LAUNCH(h);
     *grid_out = grid;
     return BP_OK;
@@ -346,10 +366,15 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
     if (rc) return rc;
     double *d_partials = (double *)h->d_buf[BP_SLOT_PARTIALS];
     int nparts = 0;
+    if (!h->d_counter) {   // arrival counter of the fused finish: zero once, every launch leaves it at zero
+        BP_CUDA(h, cudaMalloc((void **)&h->d_counter, sizeof(unsigned int)));
+        BP_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
+    }
+    // one kernel covers the whole range (the usual case: full permanents and 64-aligned shards): its last block finishes
+    const bool single = bulk ? (blo == lo && bhi == hi) : (hi > lo);
+    unsigned int *d_counter = single ? h->d_counter : nullptr;
     if (bulk) {
         const size_t bytes = sizeof(double2) * (size_t)N * N;
-        if ((rc = bp_reserve(h, BP_SLOT_MISC, bytes + 64))) return rc;
-        double *d_twice = (double *)h->d_buf[BP_SLOT_MISC];
         const uint64_t total = bhi - blo;
         const int bthreads = g_k1_bulk_threads[N];
         const uint64_t threads = (uint64_t)bulk_grid_max * bthreads;
@@ -367,10 +392,8 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
             } else {
                 BP_CUDA(h, cudaStreamWaitEvent(h->stream, g_const_event[h->device], 0));   // previous user of c_A2
             }
-            k1b_double_kernel<<<(2 * N * N + 255) / 256, 256, 0, h->stream>>>(dA, 2 * N * N, d_twice);
-            BP_CHECK_LAUNCH(h);
-            BP_CUDA(h, cudaMemcpyToSymbolAsync(c_A2, d_twice, bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
-            g_k1_bulk[N]<<<grid, bthreads, 0, h->stream>>>(dA, blo, bhi, span, d_partials);
+            BP_CUDA(h, cudaMemcpyToSymbolAsync(c_A2, dA, bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
+            g_k1_bulk[N]<<<grid, bthreads, 0, h->stream>>>(dA, blo, bhi, span, d_partials, d_counter, d_out_dd);
             BP_CHECK_LAUNCH(h);
             BP_CUDA(h, cudaEventRecord(g_const_event[h->device], h->stream));
         }
@@ -378,19 +401,20 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
     }
     if (blo > lo) {   // head (everything when the bulk path is not taken)
         int g = 0;
-        if ((rc = k1_generic(h, dA, N, lo, blo, d_partials + 4 * nparts, &g))) return rc;
+        if ((rc = k1_generic(h, dA, N, lo, blo, d_partials + 4 * nparts, &g, d_counter, d_out_dd))) return rc;
         nparts += g;
     }
     if (hi > bhi) {   // tail
         int g = 0;
-        if ((rc = k1_generic(h, dA, N, bhi, hi, d_partials + 4 * nparts, &g))) return rc;
+        if ((rc = k1_generic(h, dA, N, bhi, hi, d_partials + 4 * nparts, &g, nullptr, d_out_dd))) return rc;
         nparts += g;
     }
     if (nparts == 0) {   // empty range
         BP_CUDA(h, cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 4, h->stream));
         return BP_OK;
     }
-    glynn_finish_kernel<<<1, 32, 0, h->stream>>>(d_partials, nparts, d_out_dd);
+    if (single) return BP_OK;   // the kernel's last block has written d_out_dd
+    glynn_finish_kernel<<<1, 32, 0, h->stream>>>(d_partials, nparts, N, d_out_dd);
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }
