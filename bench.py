@@ -475,7 +475,7 @@ def run_native(args):
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full
                 # capture profiles/r01_k1_n30_block4_ncu_summary.txt (the path is FP64-bound; traffic is the matrix + code)
-                "traffic": 54016,
+                "traffic": 60672,
                 "kernel": "glynn_block4_kernel<30>", "kernel_ms": k1_ms,
                 "peak_source": "bp_fp64_peak DFMA probe (64 independent DFMA per loop iteration) on this GPU in this run; nominal B200 FP64 = 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
                 "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
