@@ -130,3 +130,73 @@ def test_numpy_compatible_tape_replays_reference_decisions():
     np.random.seed(4)
     tape = numpy_compatible_tape(sum(s), 12, orc.binomial_weights(sum(s), 0.6))
     assert np.array_equal(np.array(orc.gccb_uniform_losses_simulate(U, s, 0.6, tape)), np.array(want))
+
+
+class _OraclePermanents:
+    """Stand-in for the native handle in CPU tests of the host-side sampling logic: the batched permanents
+    come from the oracle (test infrastructure) instead of kernel K2."""
+
+    def perm_batched(self, U, S, T, formula=None):
+        from oracle import pyoracle as orc
+        return np.array([orc.guan_permanent(U, S[b].astype(np.int32), T[b].astype(np.int32), orc.CHIN_HUH, "d")
+                         for b in range(S.shape[0])], dtype=np.complex128)
+
+
+def test_gcc_host_loop_reproduces_reference_samples_with_oracle_permanents(golden_dir, monkeypatch):
+    """Host logic of the GCC (version A) strategy on the CPU: layer memo, speculative prefetch, the draw loop on cached
+    Python floats and the consumption of numpy's generator must reproduce the reference's BASELINE config 1 run
+    (tests/golden/gcc_samples.npz) when the layer permanents are exact.  (The GPU test of the same name checks the
+    same fixture with kernel K2 underneath.)"""
+    from theboss_b200 import _native
+    from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy
+    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+
+    class Calc:   # minimal calculator interface: the strategy only reads .matrix (and .device)
+        def __init__(self, U):
+            self.matrix = U
+
+    z = np.load(os.path.join(golden_dir, "gcc_samples.npz"))
+    for name in ("c1_glynn", "bunched_ryser"):
+        U, s = z[f"{name}_U"], [int(x) for x in z[f"{name}_s"]]
+        ref = z[f"{name}_samples"].astype(np.int64)
+        strat = GeneralizedCliffordsSimulationStrategy(Calc(U.copy()))
+        np.random.seed(7)
+        got = np.array(strat.simulate(s, ref.shape[0]))
+        assert np.array_equal(got, ref), name
+        for kk, vv in zip(z[f"{name}_pmf_keys"], z[f"{name}_pmf_vals"]):
+            assert np.abs(strat.pmfs[tuple(int(x) for x in kk)] - vv).max() <= 1e-12 * vv.max()
+        # a second run on the same object starts from an empty memo and draws the same samples again
+        np.random.seed(7)
+        assert np.array_equal(np.array(strat.simulate(s, 50)), ref[:50]), name
+
+
+def test_exact_distribution_host_logic_with_oracle_permanents(golden_dir, monkeypatch):
+    """Host logic of the exact distribution calculators (outcome enumeration, lossy-input weights, normalisation,
+    binomial loss weights) on the CPU against the reference's literal 56-entry vector
+    (tests/test_exact_distribution_calculator.py:75-142 in the reference) and against sum = 1."""
+    import json
+    from tests import workloads
+    from theboss_b200 import _native
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.bs_permanent_calculator_factory import (
+        BSPermanentCalculatorFactory, PermanentCalculatorType)
+    from theboss_b200.distribution_calculators.bs_exact_distribution_with_uniform_losses import (
+        BosonSamplingExperimentConfiguration, BSDistributionCalculatorWithFixedLosses, BSDistributionCalculatorWithUniformLosses)
+    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+
+    def config(U, s, lost=0, eta=1.0):
+        return BosonSamplingExperimentConfiguration(
+            interferometer_matrix=U, initial_state=list(s), initial_number_of_particles=int(sum(s)), number_of_modes=len(s),
+            number_of_particles_lost=lost, number_of_particles_left=int(sum(s)) - lost, uniform_transmissivity=eta)
+
+    with open(os.path.join(golden_dir, "exact_distribution.json")) as f:
+        g = json.load(f)
+    P = np.array(g["matrix_real"], dtype=np.complex128)
+    calc = BSPermanentCalculatorFactory(None, None, None, PermanentCalculatorType.CHIN_HUH).generate_calculator()
+    dist = BSDistributionCalculatorWithUniformLosses(config(P, g["initial_state"], lost=2, eta=g["eta"]), calc).calculate_distribution()
+    assert len(dist) == 56
+    assert np.allclose(dist, g["reference_literal"])
+    assert np.allclose(dist, g["reference_computed"], rtol=1e-12, atol=1e-15)
+    U = workloads.haar(4, 31)
+    for state, lost in (([3, 1, 2, 0], 0), ([3, 1, 2, 0], 2)):
+        assert abs(sum(BSDistributionCalculatorWithFixedLosses(config(U, state, lost), calc).calculate_distribution()) - 1) < 1e-10
+        assert abs(sum(BSDistributionCalculatorWithUniformLosses(config(U, state, lost, eta=0.7), calc).calculate_distribution()) - 1) < 1e-10
