@@ -477,7 +477,7 @@ def run_native(args):
                 # capture profiles/r01_k1_n30_block4_ncu_summary.txt (the path is FP64-bound; traffic is the matrix + code)
                 "traffic": 60672,
                 "kernel": "glynn_block4_kernel<30>", "kernel_ms": k1_ms,
-                "peak_source": "bp_fp64_peak DFMA probe (64 independent DFMA per loop iteration) on this GPU in this run; nominal B200 FP64 = 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s",
+                "peak_source": "bp_fp64_peak DFMA probe (64 independent DFMA per loop iteration) on this GPU in this run; nominal B200 FP64 = 148 SM x 64 DFMA/clk x 1.965 GHz = 37.2 TFLOP/s (MEASURED_PEAKS.json carries HBM and bf16 figures only; this path moves 60 KB of DRAM traffic per launch)",
                 "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                 "fp64_issue_slot_frac": (ISSUE_SLOTS * (job.hi - job.lo) / 2.0 ** (N_PHOTONS - 1)) * 2 / (k1_ms * 1e-3) / 1e12 / fp64_peak,
                 "structural_ceiling": (8 * N_PHOTONS - 4) / (12 * N_PHOTONS - 4),
