@@ -15,7 +15,8 @@ JSON keys beyond the base contract:
                 achieved = (8N-4)*2^(N-1) algorithmic flops / CUDA-event kernel time,
                 peak = DFMA probe measured on the same GPU in the same run (bp_fp64_peak).
   cpu_baseline  the CPU oracle port (oracle/bossperm_oracle.c, double precision, all host threads)
-                on a bounded sample of the same workload.
+                on a bounded sample of the same workload; `reference_python` quotes the committed timings
+                of the unmodified Python reference (build container, profiles/r01_reference_python_cpu.json).
   e2e           the same metric through the public API with HOST buffers
                 (ShardedGlynnPermanent.compute: H2D of the matrix and D2H of the partials inside).
   extra         secondary throughputs of the same path (other BASELINE configs), informational.
@@ -111,6 +112,29 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_python_fixture():
+    """The UNMODIFIED Python reference, timed in the build container by scripts/time_reference_python.py and
+    committed as profiles/r01_reference_python_cpu.json (the GPU box has no /root/reference and the reference
+    needs hours per n=30 permanent).  Quoted verbatim next to the live CPU-port number, never mixed into it."""
+    path = os.path.join(REPO, "profiles", "r01_reference_python_cpu.json")
+    try:
+        with open(path) as f:
+            ref = json.load(f)
+        c4, ac = ref["single_core"]["c4_glynn_single_permanent"], ref["all_cores"]
+        return {
+            "source": "profiles/r01_reference_python_cpu.json (scripts/time_reference_python.py; NOT measured on this box)",
+            "host": ref["host"],
+            "n20_permanents_per_s_1core": c4["20"]["permanents_per_s"],
+            "n30_permanents_per_s_1core_extrapolated": c4["30_extrapolated"]["permanents_per_s"],
+            "n30_permanents_per_s_all_cores_extrapolated": ac["c4_glynn_single_permanent"]["n30_extrapolated_permanents_per_s"],
+            "gccb_n24_samples_per_s_all_cores_extrapolated": ac["gccb_sampling_m_2n"]["n24_extrapolated_samples_per_s"],
+            "c1_gcc_n5_m10_samples_per_s_1core": ref["single_core"]["c1_gcc_n5_m10"]["samples_per_s"],
+        }
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -354,7 +378,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
+                         "reference_python": reference_python_fixture()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "ms_per_step is the time one full n=30 permanent would take on the host cores (extrapolated from the bounded sample)",
@@ -488,6 +513,7 @@ def run_native(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["reference_python"] = reference_python_fixture()
         if extra is not None:
             line["extra"] = extra
         print(json.dumps(line))
