@@ -121,6 +121,25 @@ class Handle:
                 raise AttributeError(msg)   # bs_permanent_calculator_base.py:179-180
             raise BossPermError(rc, msg)
 
+    @staticmethod
+    def _normalised(U, s, t):
+        """The C ABI reads raw buffers: C-contiguous complex128 (m, m) and int32[m] occupations, whatever the
+        caller handed in (a no-op for arrays that already have that form)."""
+        U = as_matrix(U)
+        if U.shape[0] != U.shape[1]:
+            raise AttributeError
+        m = U.shape[0]
+
+        def state(x):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray) and x.dtype == np.int32 and x.shape == (m,) and x.flags.c_contiguous:
+                return x
+            if np.size(x) > m:
+                raise AttributeError
+            return as_state(x, m)
+        return U, state(s), state(t)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.bp_destroy(self._h)
@@ -176,6 +195,7 @@ class Handle:
         self._check(self._lib.bp_glynn_matrix_range_dev(self._h, C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_ptr)))
 
     def glynn_single(self, U: np.ndarray, s: np.ndarray, t: np.ndarray) -> complex:
+        U, s, t = self._normalised(U, s, t)
         out = (C.c_double * 2)()
         self._check(self._lib.bp_glynn_single(self._h, U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, out))
         return complex(out[0], out[1])
@@ -198,12 +218,14 @@ class Handle:
 
     # -- K3 ----------------------------------------------------------------------------------
     def minors(self, U: np.ndarray, s: np.ndarray, t: np.ndarray, formula: int = FORMULA_CHIN_HUH) -> np.ndarray:
+        U, s, t = self._normalised(U, s, t)
         out = np.zeros(U.shape[0], dtype=np.complex128)
         self._check(self._lib.bp_minors(self._h, U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, int(formula),
                                         out.ctypes.data))
         return out
 
     def gccb_pmf(self, U: np.ndarray, s: np.ndarray, t: np.ndarray, want_minors: bool = False):
+        U, s, t = self._normalised(U, s, t)
         m = U.shape[0]
         pmf = np.zeros(m, dtype=np.float64)
         minors = np.zeros(m, dtype=np.complex128) if want_minors else None
@@ -214,6 +236,7 @@ class Handle:
     # -- K3 + K4 -----------------------------------------------------------------------------
     def gccb_simulate(self, U: np.ndarray, s: np.ndarray, n_samples: int, eta: float = -1.0, seed: int = 0,
                       first_sample: int = 0, tape: Optional[np.ndarray] = None) -> np.ndarray:
+        U, s, _ = self._normalised(U, s, None)
         m = U.shape[0]
         out = np.zeros((int(n_samples), m), dtype=np.int32)
         tp = None
@@ -226,7 +249,6 @@ class Handle:
         self._check(self._lib.bp_gccb_simulate(self._h, U.ctypes.data, m, s.ctypes.data, int(n_samples), float(eta),
                                                int(seed) & (2 ** 64 - 1), int(first_sample), tp, out.ctypes.data))
         return out
-
 
     def gccb_simulate_batch(self, Us: np.ndarray, states: np.ndarray, seed: int = 0, first_sample: int = 0,
                             tape: Optional[np.ndarray] = None) -> np.ndarray:
