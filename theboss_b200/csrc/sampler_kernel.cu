@@ -13,6 +13,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <new>
 #include <vector>
 
 #include "bp_common.cuh"
@@ -156,6 +157,18 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     if (minors) memcpy(minors, hres, sizeof(double) * 2 * (size_t)m);
     if (pmf) memcpy(pmf, hres + 2 * (size_t)m, sizeof(double) * (size_t)m);
     return BP_OK;
+}
+
+// The C ABI never throws: host-side allocation failures of the implementation become BP_ERR_NOMEM.
+template <typename F>
+static int no_throw(bp_context *h, const char *who, F &&body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return bp_fail(h, BP_ERR_NOMEM, "%s: out of host memory", who);
+    } catch (...) {
+        return bp_fail(h, BP_ERR_INVALID, "%s: unexpected C++ exception", who);
+    }
 }
 
 extern "C" {
@@ -325,14 +338,18 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
 
 int bp_gccb_simulate(bp_handle h, const double *U, int m, const int32_t *s, int64_t n_samples, double eta, uint64_t seed,
                      int64_t first_sample, const double *tape, int32_t *out) {
-    return gccb_simulate_impl(h, U, m, s, false, n_samples, eta, seed, first_sample, tape, 0, out, "bp_gccb_simulate");
+    return no_throw(h, "bp_gccb_simulate", [&] {
+        return gccb_simulate_impl(h, U, m, s, false, n_samples, eta, seed, first_sample, tape, 0, out, "bp_gccb_simulate");
+    });
 }
 
 int bp_gccb_simulate_batch(bp_handle h, const double *Us, int m, const int32_t *states, int64_t n_samples, uint64_t seed,
                            int64_t first_sample, const double *tape, int tape_particles, int32_t *out) {
     if (tape && tape_particles < 0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate_batch: tape_particles=%d", tape_particles);
-    return gccb_simulate_impl(h, Us, m, states, true, n_samples, -1.0, seed, first_sample, tape, tape ? tape_particles : 0, out,
-                              "bp_gccb_simulate_batch");
+    return no_throw(h, "bp_gccb_simulate_batch", [&] {
+        return gccb_simulate_impl(h, Us, m, states, true, n_samples, -1.0, seed, first_sample, tape, tape ? tape_particles : 0, out,
+                                  "bp_gccb_simulate_batch");
+    });
 }
 
 }  // extern "C"
