@@ -373,13 +373,13 @@ static void k2_entry(k2_fn *fn) {
     if constexpr (N > 1) k2_entry<N - 1>(fn);
 }
 static k2_fn g_k2_fn[BP_MAX_N + 1];
-static bool g_k2_init = false;
 
 // All pointers are device pointers.  Enqueues prep + sort + one launch per distinct n; needs one
 // small D2H copy (per-n offsets) in the middle, so it synchronises the stream once.
 int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
                  long long B, double *d_out) {
-    if (!g_k2_init) { k2_entry<BP_MAX_N>(g_k2_fn); g_k2_init = true; }
+    static const bool ready = [] { k2_entry<BP_MAX_N>(g_k2_fn); return true; }();   // thread-safe one-time registration
+    (void)ready;
     if (B <= 0) return BP_OK;
     if (B > 0x7fffffffll) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: B=%lld items exceeds 2^31-1", B);
     const size_t meta_bytes = sizeof(K2Meta) * (size_t)B, order_bytes = sizeof(int) * (size_t)B;
