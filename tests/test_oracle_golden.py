@@ -157,3 +157,24 @@ def test_parallel_glynn_matches_sequential(n):
     T = 1 << (n - 1)
     parts = [orc.glynn_range(A, lo, lo + T // 4) for lo in range(0, T, T // 4)]
     assert _rel(sum(parts) / T, seq) <= 1e-14
+
+
+def test_reference_outputs_at_n14_to_n20_pin_the_oracle_and_the_large_ground_truth(golden_dir):
+    """The unmodified reference was also RUN on the C4 matrix family at the largest sizes Python finishes
+    (scripts/time_reference_python.py, N = 14 .. 20; GlynnGrayPermanentCalculator, glynn_gray_permanent_calculator.py:41-84):
+    its outputs must agree with the oracle in both precisions and -- at N = 20, the size where the two overlap --
+    with the long-double ground truth that the GPU parity tests of the n = 20 .. 30 permanents are anchored on."""
+    from tests import workloads
+    path = os.path.join(os.path.dirname(os.path.dirname(golden_dir)), "profiles", "r01_reference_python_cpu.json")
+    with open(path) as f:
+        ref = json.load(f)["single_core"]["c4_glynn_single_permanent"]
+    sizes = sorted(int(k) for k in ref if k.isdigit())
+    assert sizes and max(sizes) >= 20
+    for n in sizes:
+        want = complex(ref[str(n)]["re"], ref[str(n)]["im"])
+        A = workloads.c4_matrix(n)
+        assert _rel(orc.glynn_matrix(A, "d"), want) <= 1e-10, n     # same algorithm, same precision (summation order differs)
+        assert _rel(orc.glynn_matrix(A, "ld"), want) <= 1e-10, n    # the reference's own float64 error at N = 20 is ~1e-11
+    with open(os.path.join(golden_dir, "large_permanents.json")) as f:
+        big = json.load(f)["glynn_n20"]
+    assert _rel(complex(big["re"], big["im"]), complex(ref["20"]["re"], ref["20"]["im"])) <= 1e-10
