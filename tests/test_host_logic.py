@@ -141,6 +141,19 @@ class _OraclePermanents:
         return np.array([orc.guan_permanent(U, S[b].astype(np.int32), T[b].astype(np.int32), orc.CHIN_HUH, "d")
                          for b in range(S.shape[0])], dtype=np.complex128)
 
+    def gccb_simulate_batch(self, Us, states, seed=0, first_sample=0, tape=None):
+        """One GCC-B sample per (matrix, input state) pair through the oracle's sampling loop; the decisions come from a
+        NumPy generator keyed by the seed (the device uses Philox: same distribution, different stream)."""
+        from oracle import pyoracle as orc
+        rng = np.random.RandomState(int(seed) % 2 ** 32)
+        out = np.zeros(states.shape, dtype=np.int32)
+        for i in range(states.shape[0]):
+            n = int(states[i].sum())
+            if n:
+                row = rng.random_sample((1, 1 + 2 * n)) if tape is None else tape[i:i + 1, : 1 + 2 * n]
+                out[i] = orc.gccb_simulate(Us[i], states[i], row)[0]
+        return out
+
 
 def test_gcc_host_loop_reproduces_reference_samples_with_oracle_permanents(golden_dir, monkeypatch):
     """Host logic of the GCC (version A) strategy on the CPU: layer memo, speculative prefetch, the draw loop on cached
@@ -200,3 +213,34 @@ def test_exact_distribution_host_logic_with_oracle_permanents(golden_dir, monkey
     for state, lost in (([3, 1, 2, 0], 0), ([3, 1, 2, 0], 2)):
         assert abs(sum(BSDistributionCalculatorWithFixedLosses(config(U, state, lost), calc).calculate_distribution()) - 1) < 1e-10
         assert abs(sum(BSDistributionCalculatorWithUniformLosses(config(U, state, lost, eta=0.7), calc).calculate_distribution()) - 1) < 1e-10
+
+
+def test_bobs_host_logic_matches_reference_frequencies_with_oracle_sampling(monkeypatch):
+    """Row f1 on the CPU: the vectorised per-sample input states and matrices of the two BOBS strategies (random approximated
+    mode, binomial thinning, random phases x QFT, column permutations, SVD-free dilation) must give the outcome statistics of
+    the UNMODIFIED reference (tests/golden/bobs_frequencies.json, 50 000 samples per case from
+    tests/golden/make_bobs_golden.py) when the per-sample GCC-B draw underneath is exact (oracle loop).  The GPU test
+    tests/test_gpu_zz_bobs_reference_statistics.py checks the same fixture with bp_gccb_simulate_batch underneath."""
+    from tests import bobs_cases
+    from theboss_b200 import _native
+    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+    ref_samples, cases = bobs_cases.load_cases()
+    N = 12000
+    for i, (name, case) in enumerate(cases.items()):
+        K = bobs_cases.outcomes_count(case)
+        bound = bobs_cases.tvd_bound(K, N) + bobs_cases.tvd_bound(K, ref_samples)
+        np.random.seed(50 + i)
+        samples = bobs_cases.build_strategy(case).simulate(case["state"], N)
+        assert len(samples) == N and all(len(x) == len(case["state"]) for x in samples[:10])
+        tvd = bobs_cases.tvd_to_reference(samples, case)
+        assert tvd <= bound, (name, tvd, bound)                                  # the reference's own acceptance criterion
+        p = bobs_cases.chi2_pvalue(samples, case, ref_samples)
+        assert p > 1e-6, (name, p)                                               # the sharper two-sample test
+    # power of the check: a strategy with one parameter off is rejected (p-values measured: 1e-18 ... 1e-90)
+    wrong = [("nla_m5_k2", dict(approximated_modes=0)), ("nla_m5_k2", dict(etas=[0.6, 0.6, 0.7, 0.8, 0.9])),
+             ("lsa_m5_hl2", dict(eta=0.65)), ("lsa_m4_hl3_bunched", dict(hierarchy_level=2))]
+    for name, override in wrong:
+        case = cases[name]
+        np.random.seed(7)
+        samples = bobs_cases.build_strategy(case, **override).simulate(case["state"], N)
+        assert bobs_cases.chi2_pvalue(samples, case, ref_samples) < 1e-9, (name, override)

@@ -316,8 +316,6 @@ static void k1_entry(k1_fn *fn, int *minb, k1_fn *bulk) {
     if constexpr (N > 1) k1_entry<N - 1>(fn, minb, bulk);
 }
 
-static bool g_k1_init = false;
-
 // c_A2 is one slot per device: uses are ordered by a host mutex plus an event the next writer waits on.
 static std::mutex g_const_mutex;
 static cudaEvent_t g_const_event[64];
@@ -343,15 +341,13 @@ static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint6
 // Enqueue K1 over Gray steps [lo, hi) of an N x N device matrix; d_out_dd receives the
 // un-normalised double-double partial.
 int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_out_dd) {
-    if (!g_k1_init) {
-        std::lock_guard<std::mutex> g(g_const_mutex);
-        if (!g_k1_init) {
-            k1_entry<BP_MAX_N>(g_k1_fn, g_k1_minb, g_k1_bulk);
-            if (const char *e = getenv("BP_K1_BULK_MAX_N"))   // tuning: generic kernel above this N
-                for (int n = atoi(e) + 1; n <= BP_MAX_N; ++n) if (n >= 1) g_k1_bulk[n] = nullptr;
-            g_k1_init = true;
-        }
-    }
+    static const bool ready = [] {   // thread-safe one-time registration of the template instances
+        k1_entry<BP_MAX_N>(g_k1_fn, g_k1_minb, g_k1_bulk);
+        if (const char *e = getenv("BP_K1_BULK_MAX_N"))   // tuning: generic kernel above this N
+            for (int n = atoi(e) + 1; n <= BP_MAX_N; ++n) if (n >= 1) g_k1_bulk[n] = nullptr;
+        return true;
+    }();
+    (void)ready;
     if (N < 1 || N > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "K1 supports 1 <= N <= %d, got %d", BP_MAX_N, N);
     const uint64_t total_terms = 1ull << (N - 1);
     if (lo > hi || hi > total_terms) return bp_fail(h, BP_ERR_INVALID, "Gray step range [%llu, %llu) outside [0, 2^%d)",

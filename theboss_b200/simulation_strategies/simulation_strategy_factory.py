@@ -44,10 +44,13 @@ _OUT_OF_SCOPE = {
 
 class SimulationStrategyFactory:
     def __init__(self, experiment_configuration, bs_permanent_calculator,
-                 strategy_type: StrategyType = StrategyType.GCC) -> None:
+                 strategy_type: StrategyType = StrategyType.FIXED_LOSS) -> None:   # same default as the reference (:52)
         self.experiment_configuration = experiment_configuration
         self.strategy_type = strategy_type
         self._bs_permanent_calculator = deepcopy(bs_permanent_calculator)
+        # :74, :79-85 of the reference: size of the BOBS process pool.  Kept so that callers can set it; the samples of a
+        # request run as one GPU batch here, so the value is not used.
+        self.available_threads_number = -1
 
     @property
     def bs_permanent_calculator(self):
