@@ -10,7 +10,7 @@ share with them: parity of this row is statistical.  The script calls the per-wo
 lossy_state_approximated_simulation_strategy.py:287-310) in THIS process after doing what `simulate` does before it
 fans out to its spawn pool (:215-257 resp. :96-118) -- same code, same distributions, but seedable and without
 16 interpreter start-ups -- and stores the observed frequency of every outcome in `bobs_frequencies.json`.
-tests/test_host_logic.py (oracle permanents underneath, CPU) and tests/test_gpu_zz_bobs_reference_statistics.py
+tests/test_host_logic.py (oracle permanents underneath, CPU) and tests/test_gpu_zz_reference_runs.py
 (CUDA kernels underneath) compare the drop-in strategies against these frequencies.
 """
 import json

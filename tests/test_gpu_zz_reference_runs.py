@@ -1,4 +1,5 @@
-"""Row f1 of SURVEY.md section 8(f) against the reference itself: outcome statistics of the two BOBS strategies, with
+"""Rows f1 and f3 of SURVEY.md section 8(f) against runs of the reference itself (this module sorts last on purpose: it
+was added after the last GPU visit of round 1).  f3: see the last test.  f1: outcome statistics of the two BOBS strategies, with
 bp_gccb_simulate_batch (one matrix + one input state per sample, Philox decisions) underneath, against the frequencies the
 UNMODIFIED reference produced on the same seeded networks (tests/golden/bobs_frequencies.json, 50 000 samples per case,
 tests/golden/make_bobs_golden.py).  The strategies draw fresh random phases, permutations and lossy inputs per sample, so
@@ -30,3 +31,10 @@ def test_bobs_strategy_matches_reference_frequencies(name):
     # sharper: two-sample chi-square; wrong parameters give p < 1e-18 already at 12 000 samples (tests/test_host_logic.py)
     p = bobs_cases.chi2_pvalue(samples, case, _REF_SAMPLES)
     assert p > 1e-6, (name, p)
+
+
+def test_version_a_uniform_losses_sampler_reproduces_reference_samples(golden_dir):
+    """Row f3 against the reference itself (tests/golden/gcc_uniform_losses_samples.npz): identical seeds of the stdlib
+    and NumPy generators give the reference's samples bit for bit, with the layer permanents from kernel K2."""
+    from tests.test_host_logic import _check_uniform_losses_a_fixture
+    _check_uniform_losses_a_fixture(golden_dir)

@@ -220,7 +220,7 @@ def test_bobs_host_logic_matches_reference_frequencies_with_oracle_sampling(monk
     mode, binomial thinning, random phases x QFT, column permutations, SVD-free dilation) must give the outcome statistics of
     the UNMODIFIED reference (tests/golden/bobs_frequencies.json, 50 000 samples per case from
     tests/golden/make_bobs_golden.py) when the per-sample GCC-B draw underneath is exact (oracle loop).  The GPU test
-    tests/test_gpu_zz_bobs_reference_statistics.py checks the same fixture with bp_gccb_simulate_batch underneath."""
+    tests/test_gpu_zz_reference_runs.py checks the same fixture with bp_gccb_simulate_batch underneath."""
     from tests import bobs_cases
     from theboss_b200 import _native
     monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
@@ -244,3 +244,38 @@ def test_bobs_host_logic_matches_reference_frequencies_with_oracle_sampling(monk
         np.random.seed(7)
         samples = bobs_cases.build_strategy(case, **override).simulate(case["state"], N)
         assert bobs_cases.chi2_pvalue(samples, case, ref_samples) < 1e-9, (name, override)
+
+
+def _check_uniform_losses_a_fixture(golden_dir):
+    """Shared by the CPU (oracle permanents) and GPU (kernel K2) tests of row f3: same seeds of the stdlib and NumPy
+    generators as tests/golden/make_uniform_losses_a_golden.py -> the reference's samples bit for bit, and the recorded
+    distributions to 1e-12."""
+    import random
+    from theboss_b200.simulation_strategies.generalized_cliffords_uniform_losses_simulation_strategy import (
+        GeneralizedCliffordsUniformLossesSimulationStrategy)
+
+    class Calc:
+        def __init__(self, U):
+            self.matrix = U
+
+    z = np.load(os.path.join(golden_dir, "gcc_uniform_losses_samples.npz"))
+    assert len(z["names"]) == 3
+    for name in z["names"]:
+        U, s, eta = z[f"{name}_U"], [int(x) for x in z[f"{name}_s"]], float(z[f"{name}_eta"])
+        ref = z[f"{name}_samples"]
+        strat = GeneralizedCliffordsUniformLossesSimulationStrategy(Calc(U.copy()), eta)
+        random.seed(int(z[f"{name}_seeds"][0]))
+        np.random.seed(int(z[f"{name}_seeds"][1]))
+        got = np.array(strat.simulate(s, ref.shape[0]))
+        assert np.array_equal(got, ref), name
+        assert np.allclose(strat.distribution, z[f"{name}_distribution"], rtol=1e-12, atol=1e-15), name
+        assert np.allclose(strat.unweighted_distribution, z[f"{name}_unweighted"], rtol=1e-12, atol=1e-15), name
+
+
+def test_version_a_uniform_losses_host_loop_reproduces_reference_samples(golden_dir, monkeypatch):
+    """Row f3 on the CPU: per-particle stdlib `random.random()` loss draws, NumPy draws for the kept particles, layer memo
+    and the distribution bookkeeping of generalized_cliffords_uniform_losses_simulation_strategy.py:126-173 in the
+    reference, with exact (oracle) layer permanents underneath."""
+    from theboss_b200 import _native
+    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+    _check_uniform_losses_a_fixture(golden_dir)
