@@ -1,0 +1,47 @@
+"""pytest plugin that points the REFERENCE's own test modules at the drop-in package.
+
+    PYTHONPATH=/root/repo python -m pytest -p oracle.reference_suite_plugin /root/reference/tests
+
+(build container only: needs /root/reference; driven by tests/test_reference_suite_cpu.py).  Every module of ``theboss``
+that ``theboss_b200`` rebuilds (same relative module path) is registered in ``sys.modules`` under its reference name, so
+``from theboss.simulation_strategies.simulation_strategy_factory import ...`` in the reference's tests resolves to the
+drop-in; modules outside the permanent hot path (mean-field strategies, TVD helpers, network simulation) stay the
+reference's own.  There is no GPU in the build container, so the arithmetic underneath comes from the CPU oracle through
+oracle/handle_standin.py: what this run checks is the API surface and host logic of the drop-in, not the kernels.
+"""
+import importlib
+import os
+import pkgutil
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("THEBOSS_REFERENCE", "/root/reference")
+for p in (os.path.join(REPO, "oracle", "refshim"), REPO, REF):   # REF first: `tests` must be the reference's package
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import theboss  # noqa: E402  (the reference package: parent of the aliased modules)
+import theboss_b200  # noqa: E402
+from theboss_b200 import _native  # noqa: E402
+from oracle import handle_standin as oracle_handle  # noqa: E402
+
+ALIASED = []
+for info in pkgutil.walk_packages(theboss_b200.__path__, "theboss_b200."):
+    rel = info.name[len("theboss_b200."):]
+    if info.ispkg or rel.split(".")[-1].startswith("_") or rel == "distributed":
+        continue
+    if not os.path.exists(os.path.join(REF, "theboss", *rel.split(".")) + ".py"):
+        continue
+    module = importlib.import_module(info.name)
+    sys.modules["theboss." + rel] = module
+    parent = importlib.import_module("theboss." + rel.rsplit(".", 1)[0]) if "." in rel else theboss
+    setattr(parent, rel.rsplit(".", 1)[-1], module)
+    ALIASED.append(rel)
+
+_HANDLE = oracle_handle.OracleHandle()
+_native.default_handle = lambda device=0: _HANDLE
+
+
+def pytest_terminal_summary(terminalreporter):
+    terminalreporter.write_line(f"theboss -> theboss_b200 for {len(ALIASED)} modules: " + ", ".join(sorted(ALIASED)))
+    terminalreporter.write_line(f"oracle-backed handle served {_HANDLE.calls} calls from the drop-in package")

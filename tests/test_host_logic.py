@@ -132,27 +132,11 @@ def test_numpy_compatible_tape_replays_reference_decisions():
     assert np.array_equal(np.array(orc.gccb_uniform_losses_simulate(U, s, 0.6, tape)), np.array(want))
 
 
-class _OraclePermanents:
-    """Stand-in for the native handle in CPU tests of the host-side sampling logic: the batched permanents
-    come from the oracle (test infrastructure) instead of kernel K2."""
-
-    def perm_batched(self, U, S, T, formula=None):
-        from oracle import pyoracle as orc
-        return np.array([orc.guan_permanent(U, S[b].astype(np.int32), T[b].astype(np.int32), orc.CHIN_HUH, "d")
-                         for b in range(S.shape[0])], dtype=np.complex128)
-
-    def gccb_simulate_batch(self, Us, states, seed=0, first_sample=0, tape=None):
-        """One GCC-B sample per (matrix, input state) pair through the oracle's sampling loop; the decisions come from a
-        NumPy generator keyed by the seed (the device uses Philox: same distribution, different stream)."""
-        from oracle import pyoracle as orc
-        rng = np.random.RandomState(int(seed) % 2 ** 32)
-        out = np.zeros(states.shape, dtype=np.int32)
-        for i in range(states.shape[0]):
-            n = int(states[i].sum())
-            if n:
-                row = rng.random_sample((1, 1 + 2 * n)) if tape is None else tape[i:i + 1, : 1 + 2 * n]
-                out[i] = orc.gccb_simulate(Us[i], states[i], row)[0]
-        return out
+def _install_oracle_handle(monkeypatch):
+    """CPU stand-in for the native handle (oracle/handle_standin.py): the arithmetic below the C-ABI boundary comes from
+    the oracle, so that the host-side logic above it can be tested without a GPU."""
+    from oracle import handle_standin
+    return handle_standin.install(monkeypatch)
 
 
 def test_gcc_host_loop_reproduces_reference_samples_with_oracle_permanents(golden_dir, monkeypatch):
@@ -162,7 +146,7 @@ def test_gcc_host_loop_reproduces_reference_samples_with_oracle_permanents(golde
     same fixture with kernel K2 underneath.)"""
     from theboss_b200 import _native
     from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy
-    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+    _install_oracle_handle(monkeypatch)
 
     class Calc:   # minimal calculator interface: the strategy only reads .matrix (and .device)
         def __init__(self, U):
@@ -194,7 +178,7 @@ def test_exact_distribution_host_logic_with_oracle_permanents(golden_dir, monkey
         BSPermanentCalculatorFactory, PermanentCalculatorType)
     from theboss_b200.distribution_calculators.bs_exact_distribution_with_uniform_losses import (
         BosonSamplingExperimentConfiguration, BSDistributionCalculatorWithFixedLosses, BSDistributionCalculatorWithUniformLosses)
-    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+    _install_oracle_handle(monkeypatch)
 
     def config(U, s, lost=0, eta=1.0):
         return BosonSamplingExperimentConfiguration(
@@ -223,7 +207,7 @@ def test_bobs_host_logic_matches_reference_frequencies_with_oracle_sampling(monk
     tests/test_gpu_zz_reference_runs.py checks the same fixture with bp_gccb_simulate_batch underneath."""
     from tests import bobs_cases
     from theboss_b200 import _native
-    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+    _install_oracle_handle(monkeypatch)
     ref_samples, cases = bobs_cases.load_cases()
     N = 12000
     for i, (name, case) in enumerate(cases.items()):
@@ -277,5 +261,57 @@ def test_version_a_uniform_losses_host_loop_reproduces_reference_samples(golden_
     and the distribution bookkeeping of generalized_cliffords_uniform_losses_simulation_strategy.py:126-173 in the
     reference, with exact (oracle) layer permanents underneath."""
     from theboss_b200 import _native
-    monkeypatch.setattr(_native, "default_handle", lambda device=0: _OraclePermanents())
+    _install_oracle_handle(monkeypatch)
     _check_uniform_losses_a_fixture(golden_dir)
+
+
+def test_state_space_helpers():
+    """Known values of the bookkeeping helpers mirrored from the reference's boson_sampling_utilities.py (:206-261,
+    :345-502); identity with the reference's functions over a grid of sizes is part of tests/test_reference_suite_cpu.py
+    (its tests/test_boson_sampling_utilities.py runs against these)."""
+    from theboss_b200.boson_sampling_utilities import boson_sampling_utilities as bsu
+    assert bsu.bosonic_space_dimension(3, 5) == 35 and bsu.bosonic_space_dimension(3, 5, losses=True) == 1 + 5 + 15 + 35
+    assert bsu.bosonic_space_dimension(0, 4) == 1
+    assert bsu.generate_state_types(3, 4) == [(4, 0, 0), (3, 1, 0), (2, 1, 1), (2, 2, 0)]
+    assert bsu.generate_state_types(2, 2, losses=True) == [(2, 0), (1, 1), (0, 0), (1, 0)]
+    assert [bsu.compute_number_of_k_element_integer_partitions_of_n(k, 7) for k in range(1, 8)] == [1, 3, 4, 3, 2, 1, 1]
+    for m, n, losses in ((3, 4, False), (5, 6, True), (2, 7, True)):
+        types = bsu.generate_state_types(m, n, losses)
+        assert bsu.compute_number_of_state_types(m, n, losses) == len(types)
+        # every Fock state belongs to exactly one type
+        assert sum(bsu.compute_number_of_states_of_given_type(t) for t in types) == bsu.bosonic_space_dimension(n, m, losses)
+    assert bsu.compute_number_of_states_of_given_type((2, 1, 1, 0)) == 12
+    lossy = __import__("tests.workloads", fromlist=["haar"]).haar(4, 9) @ np.diag(np.sqrt([0.2, 0.5, 0.9, 1.0]))
+    assert np.allclose(bsu.get_modes_transmissivity_values_from_matrix(lossy), [0.2, 0.5, 0.9, 1.0])
+
+
+def test_distribution_calculator_snapshots_its_configuration(monkeypatch):
+    """bs_distribution_calculator_with_fixed_losses.py:41 of the reference deep-copies the configuration; its tests rely on
+    that (they re-point `initial_state` of the object they passed in before asking for the distribution)."""
+    from tests import workloads
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.chin_huh_permanent_calculator import ChinHuhPermanentCalculator
+    from theboss_b200.distribution_calculators.bs_exact_distribution_with_uniform_losses import (
+        BosonSamplingExperimentConfiguration, BSDistributionCalculatorWithUniformLosses)
+    _install_oracle_handle(monkeypatch)
+    U = workloads.haar(3, 5)
+    cfg = BosonSamplingExperimentConfiguration(interferometer_matrix=U, initial_state=[1, 1, 0], initial_number_of_particles=2,
+                                               number_of_modes=3, number_of_particles_lost=0, number_of_particles_left=2,
+                                               uniform_transmissivity=0.7)
+    calc = BSDistributionCalculatorWithUniformLosses(cfg, ChinHuhPermanentCalculator(U))
+    before = calc.calculate_distribution()
+    cfg.initial_state, cfg.uniform_transmissivity = [0, 0, 2], 0.1
+    assert calc.configuration is not cfg and list(calc.configuration.initial_state) == [1, 1, 0]
+    assert np.allclose(calc.calculate_distribution(), before) and abs(sum(before) - 1) < 1e-12
+
+
+def test_strategy_factory_defaults_and_out_of_scope_members():
+    """Same default member as the reference (simulation_strategy_factory.py:52); the members that never touch a permanent
+    resolve to the reference's own classes when `theboss` is importable and raise NotImplementedError naming them when not."""
+    import sys
+    from theboss_b200.simulation_strategies import simulation_strategy_factory as ssf
+    factory = ssf.SimulationStrategyFactory(None, None)
+    assert factory.strategy_type == ssf.StrategyType.FIXED_LOSS and factory.available_threads_number == -1
+    assert [t.value for t in ssf.StrategyType] == list(range(1, 10))
+    if "theboss" not in sys.modules and not any(os.path.isdir(os.path.join(p, "theboss")) for p in sys.path if p):
+        with pytest.raises(NotImplementedError, match="FixedLossSimulationStrategy"):
+            factory.generate_strategy()

@@ -1,18 +1,23 @@
-"""Host-side helpers of the permanent path (NumPy), mirroring the three functions of the reference's
-``theboss/boson_sampling_utilities/boson_sampling_utilities.py`` that the hot path touches:
+"""Host-side helpers of the permanent path (NumPy), mirroring the functions of the reference's
+``theboss/boson_sampling_utilities/boson_sampling_utilities.py`` that the hot path and its callers touch:
 
 * ``mode_occupation_to_mode_assignment``                 (:61-78)
 * ``prepare_interferometer_matrix_in_expanded_space``    (:287-342, helper :263-284)
 * ``EffectiveScatteringMatrixCalculator``                (:545-626)
 * ``generate_possible_states`` / ``generate_lossy_n_particle_input_states`` (:81-203), needed by the exact
   distribution calculators that sit on top of the batched permanent kernel
+* the state-space bookkeeping helpers its callers and tests import from the same module (``bosonic_space_dimension``,
+  ``get_modes_transmissivity_values_from_matrix``, state types and their counts, :206-261, :345-502)
 
 The expansion of rows/columns by occupation is done on the device inside the kernels
 (theboss_b200/csrc/util_kernels.cu, guan_kernel.cu); the class below exists for API compatibility and
 for callers that want the explicit matrix.
 """
+import functools
 import itertools
-from typing import List, Optional, Sequence, Tuple
+from collections import Counter
+from math import comb, factorial
+from typing import Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -72,6 +77,66 @@ def generate_lossy_n_particle_input_states(initial_state: Sequence[int], number_
             seen.add(occ)
             out.append(occ)
     return out
+
+
+def bosonic_space_dimension(particles_number: int, modes_number: int, losses: bool = False) -> int:
+    """Number of m-mode Fock states with exactly n particles (stars and bars), or with at most n when ``losses``
+    (reference :206-237)."""
+    fewest = 0 if losses else particles_number
+    return sum(comb(n + modes_number - 1, n) for n in range(fewest, particles_number + 1))
+
+
+def get_modes_transmissivity_values_from_matrix(lossy_interferometer_matrix) -> np.ndarray:
+    """Squared singular values of a (lossy) interferometer, smallest first; like the reference (:240-261) the order
+    is the SVD's, not the modes'."""
+    sv = np.linalg.svd(np.asarray(lossy_interferometer_matrix, dtype=np.complex128), compute_uv=False)
+    return np.square(sv[::-1])
+
+
+def _ascending_partitions(n: int, smallest: int = 1) -> Iterator[Tuple[int, ...]]:
+    """Integer partitions of n with non-decreasing parts >= ``smallest``: the one-part partition first, then by first part."""
+    yield (n,)
+    for first in range(smallest, n // 2 + 1):
+        for rest in _ascending_partitions(n - first, first):
+            yield (first,) + rest
+
+
+def generate_state_types(modes_number: int, particles_number: int, losses: bool = False) -> List[Tuple[int, ...]]:
+    """State types (occupations up to mode permutations, written in non-increasing order and padded with zeros) of n
+    particles in m modes; with ``losses`` followed by those of 0, 1, ..., n - 1 particles (reference :345-400)."""
+    counts = [particles_number] + (list(range(particles_number)) if losses else [])
+    types = []
+    for n in counts:
+        for parts in _ascending_partitions(n):
+            if len(parts) <= modes_number:
+                types.append(tuple(sorted(parts, reverse=True)) + (0,) * (modes_number - len(parts)))
+    return types
+
+
+@functools.lru_cache(maxsize=None)
+def compute_number_of_k_element_integer_partitions_of_n(k: int, n: int) -> int:
+    """p_k(n) by the recurrence p_k(n) = p_k(n - k) + p_{k-1}(n - 1), with the reference's conventions at the edges
+    (:478-502): one 1-element partition for every n (also n = 0), none when k > n, n = 0 or k < 1."""
+    if k == 1:
+        return 1
+    if k > n or n == 0 or k < 1:
+        return 0
+    return (compute_number_of_k_element_integer_partitions_of_n(k, n - k)
+            + compute_number_of_k_element_integer_partitions_of_n(k - 1, n - 1))
+
+
+def compute_number_of_state_types(modes_number: int, particles_number: int, losses: bool = False) -> int:
+    """Number of partitions of n into at most m parts; with ``losses`` summed over 0 .. n particles (reference :403-441)."""
+    counts = range(particles_number + 1) if losses else [particles_number]
+    return sum(compute_number_of_k_element_integer_partitions_of_n(k, n) for n in counts for k in range(1, modes_number + 1))
+
+
+def compute_number_of_states_of_given_type(state_type: Sequence[int]) -> int:
+    """Distinct mode permutations of a state type: m! / prod(multiplicity of each occupation value)! (reference :444-475)."""
+    number = factorial(len(state_type))
+    for multiplicity in Counter(state_type).values():
+        number //= factorial(multiplicity)
+    return number
 
 
 def prepare_interferometer_matrix_in_expanded_space(interferometer_matrix) -> np.ndarray:

@@ -8,6 +8,7 @@ K2 (``bp_perm_batched``) using the matrix held by the injected calculator, and t
 :99-106 / :139-151 are applied on the host.
 """
 import math
+from copy import deepcopy
 from typing import Iterable, List, Tuple
 
 import numpy as np
@@ -26,7 +27,9 @@ from .bs_distribution_calculator_interface import (
 
 class BSDistributionCalculatorWithFixedLosses(BSDistributionCalculatorInterface):
     def __init__(self, configuration: BosonSamplingExperimentConfiguration, permanent_calculator) -> None:
-        self.configuration = configuration
+        # a snapshot, like the reference (:41): its tests go on mutating the configuration they passed in
+        # (tests/gcc_based_strategies_tests_base.py:84-91) and the calculator must keep describing the original experiment
+        self.configuration = deepcopy(configuration)
         self._permanent_calculator = permanent_calculator
 
     @property
