@@ -1,0 +1,160 @@
+"""Differential run of the reference's calculators and the drop-in classes on the same inputs, edge cases included
+(build container only: imports the unmodified reference from /root/reference; the arithmetic under the drop-in comes from
+the CPU stand-in oracle/handle_standin.py, so this pins the Python layer: accepted argument types, padding of short states,
+shortcuts, exceptions and return types).  The deliberate deviations are listed in DESIGN.md section 5."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests import workloads
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("THEBOSS_REFERENCE", "/root/reference")
+_PC = "boson_sampling_utilities.permanent_calculators."
+
+
+@pytest.fixture(scope="module")
+def reference():
+    if not os.path.isdir(os.path.join(REF, "theboss")):
+        pytest.skip("reference checkout not available on this machine")
+    import importlib
+    sys.path[:0] = [REF, os.path.join(REPO, "oracle", "refshim")]      # taken off again by _restore_path
+    return lambda name: importlib.import_module("theboss." + name)
+
+
+@pytest.fixture(autouse=True)
+def _restore_path():
+    before = list(sys.path)
+    yield
+    sys.path[:] = before
+
+
+def _outcome(f):
+    try:
+        return "ok", f()
+    except Exception as error:          # noqa: BLE001 -- the exception type is what is compared
+        return "raised", type(error).__name__
+
+
+U4 = workloads.haar(4, 3)
+SINGLE_CASES = {
+    "plain": (U4, [1, 1, 0, 1], [0, 2, 1, 0]),
+    "collision-free": (U4, [1, 1, 1, 0], [0, 1, 1, 1]),
+    "all in one mode": (U4, [0, 3, 0, 0], [0, 0, 3, 0]),
+    "no particles": (U4, [0, 0, 0, 0], [0, 0, 0, 0]),
+    "short states of equal length": (U4, [1, 1, 0], [0, 1, 1]),
+    "states of different length": (U4, [1, 1, 0], [0, 1, 1, 0]),
+    "float ndarray states": (U4, np.array([1., 0., 2., 0.]), np.array([0., 1., 1., 1.])),
+    "tuple states": (U4, (1, 0, 2, 0), (0, 1, 1, 1)),
+    "list-of-lists matrix": (U4.tolist(), [1, 0, 2, 0], [0, 1, 1, 1]),
+    "one particle": (U4, [0, 1, 0, 0], [0, 0, 1, 0]),
+    "1x1 matrix, three particles": (np.array([[0.5 + 0.5j]]), [3], [3]),
+}
+SINGLE_CLASSES = {
+    "ryser_permanent_calculator": "RyserPermanentCalculator",
+    "chin_huh_permanent_calculator": "ChinHuhPermanentCalculator",
+    "glynn_gray_permanent_calculator": "GlynnGrayPermanentCalculator",
+    "classic_permanent_calculator": "ClassicPermanentCalculator",
+}
+
+
+@pytest.mark.parametrize("module", sorted(SINGLE_CLASSES))
+def test_single_permanent_calculators_behave_like_the_reference(reference, monkeypatch, module):
+    import importlib
+    from oracle import handle_standin
+    handle_standin.install(monkeypatch)
+    ref_cls = getattr(reference(_PC + module), SINGLE_CLASSES[module])
+    our_cls = getattr(importlib.import_module("theboss_b200." + _PC + module), SINGLE_CLASSES[module])
+    for name, (M, s, t) in SINGLE_CASES.items():
+        want = _outcome(lambda: ref_cls(M, s, t).compute_permanent())
+        got = _outcome(lambda: our_cls(M, s, t).compute_permanent())
+        assert got[0] == want[0], (module, name, want, got)
+        if want[0] == "raised":
+            assert got[1] == want[1], (module, name, want, got)
+        else:
+            assert type(got[1]) is type(want[1]) is np.complex128, (module, name)
+            assert abs(got[1] - want[1]) <= 1e-10 * max(1.0, abs(want[1])), (module, name, want, got)
+    # the three properties hand back the objects they were given (reference tests mutate `calculator.matrix` in place)
+    M, s, t = U4.copy(), [1, 1, 0, 1], [0, 2, 1, 0]
+    calc = our_cls(M, s, t)
+    assert calc.matrix is M and calc.input_state is s and calc.output_state is t
+    before = calc.compute_permanent()
+    calc.matrix *= 2.0
+    assert abs(calc.compute_permanent() - before * 2 ** 3) <= 1e-10 * abs(before) * 8
+
+
+SUB_CASES = {
+    "plain": (U4, [1, 1, 0, 1], [0, 1, 1, 0]),
+    "bunched": (U4, [2, 1, 0, 1], [0, 2, 1, 0]),
+    "k = 1": (U4, [0, 1, 0, 0], [0, 0, 0, 0]),
+    "k = 1, no output state": (U4, [0, 1, 0, 0], None),
+    "float ndarray states": (U4, np.array([1., 1., 0., 1.]), np.array([0., 1., 1., 0.])),
+    "short states": (U4, [1, 1, 1], [0, 1, 1]),
+}
+SUB_CLASSES = {
+    "bs_cc_ryser_submatrices_permanent_calculator": "BSCCRyserSubmatricesPermanentCalculator",
+    "bs_cc_ch_submatrices_permanent_calculator": "BSCCCHSubmatricesPermanentCalculator",
+}
+
+
+@pytest.mark.parametrize("module", sorted(SUB_CLASSES))
+def test_submatrices_calculators_behave_like_the_reference(reference, monkeypatch, module):
+    import importlib
+    from oracle import handle_standin
+    handle_standin.install(monkeypatch)
+    ref_cls = getattr(reference(_PC + module), SUB_CLASSES[module])
+    our_cls = getattr(importlib.import_module("theboss_b200." + _PC + module), SUB_CLASSES[module])
+    for name, (M, s, t) in SUB_CASES.items():
+        want = _outcome(lambda: ref_cls(M, s, t).compute_permanents())
+        got = _outcome(lambda: our_cls(M, s, t).compute_permanents())
+        assert got[0] == want[0] == "ok", (module, name, want, got)
+        assert type(got[1]) is type(want[1]) is list and len(got[1]) == len(want[1]), (module, name)
+        assert all(type(v) is np.complex128 for v in got[1]), (module, name)
+        assert np.allclose(np.array(got[1]), np.array(want[1], dtype=complex), rtol=1e-9, atol=1e-12), (module, name, want, got)
+
+
+def test_gccb_family_replays_the_reference_under_the_same_numpy_seed(reference, monkeypatch):
+    """`rng_mode="numpy"`: the drop-in strategies consume NumPy's global generator in the reference's call order, so the same
+    seed gives the reference's samples (generalized_cliffords_b_simulation_strategy.py:94-110, the uniform-loss subclass
+    :67-121, the lossy-network wrapper :41-88), in the reference's container types."""
+    from oracle import handle_standin
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.ryser_permanent_calculator import RyserPermanentCalculator
+    from theboss_b200.simulation_strategies.generalized_cliffords_b_simulation_strategy import GeneralizedCliffordsBSimulationStrategy
+    from theboss_b200.simulation_strategies.generalized_cliffords_b_uniform_losses_simulation_strategy import (
+        GeneralizedCliffordsBUniformLossesSimulationStrategy)
+    from theboss_b200.simulation_strategies.lossy_networks_generalized_cliffords_simulation_strategy import (
+        LossyNetworksGeneralizedCliffordsSimulationStrategy)
+    handle_standin.install(monkeypatch)
+    ref_calc = reference(_PC + "ryser_permanent_calculator").RyserPermanentCalculator
+    ref_b = reference("simulation_strategies.generalized_cliffords_b_simulation_strategy").GeneralizedCliffordsBSimulationStrategy
+    ref_bu = reference("simulation_strategies.generalized_cliffords_b_uniform_losses_simulation_strategy").GeneralizedCliffordsBUniformLossesSimulationStrategy
+    ref_ln = reference("simulation_strategies.lossy_networks_generalized_cliffords_simulation_strategy").LossyNetworksGeneralizedCliffordsSimulationStrategy
+    U, s = workloads.haar(6, 21), [1, 2, 0, 1, 1, 0]
+    lossy = U @ np.diag(np.sqrt(np.linspace(0.4, 0.9, 6)))
+
+    def both(ref_strategy, our_strategy, state, seed, n=40):
+        np.random.seed(seed)
+        want = ref_strategy.simulate(state, n)
+        np.random.seed(seed)
+        got = our_strategy.simulate(state, n)
+        assert len(got) == len(want) == n
+        assert [tuple(int(v) for v in x) for x in got] == [tuple(int(v) for v in x) for x in want]
+        return want, got
+
+    want, got = both(ref_b(ref_calc(U.copy(), None, None)), GeneralizedCliffordsBSimulationStrategy(RyserPermanentCalculator(U.copy()), rng_mode="numpy"), s, 3)
+    assert type(got) is type(want) is list and type(got[0]) is type(want[0]) is tuple
+    want, got = both(ref_bu(ref_calc(U.copy(), None, None), 0.6),
+                     GeneralizedCliffordsBUniformLossesSimulationStrategy(RyserPermanentCalculator(U.copy()), 0.6, rng_mode="numpy"), np.array(s), 4)
+    assert isinstance(got[0], np.ndarray) and isinstance(want[0], np.ndarray) and got[0].dtype == want[0].dtype
+    want, got = both(ref_ln(ref_calc(lossy.copy(), None, None)),
+                     LossyNetworksGeneralizedCliffordsSimulationStrategy(RyserPermanentCalculator(lossy.copy()), rng_mode="numpy"), s, 5)
+    assert type(got[0]) is type(want[0]) is tuple and len(got[0]) == len(want[0]) == 6
+    # the generator is left in the same state: the NEXT draw agrees too
+    np.random.seed(9)
+    ref_b(ref_calc(U.copy(), None, None)).simulate(s, 3)
+    after_ref = np.random.random()
+    np.random.seed(9)
+    GeneralizedCliffordsBSimulationStrategy(RyserPermanentCalculator(U.copy()), rng_mode="numpy").simulate(s, 3)
+    assert np.random.random() == after_ref
