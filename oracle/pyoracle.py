@@ -15,7 +15,7 @@ import ctypes as C
 import os
 import subprocess
 from math import factorial
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import numpy as np
 

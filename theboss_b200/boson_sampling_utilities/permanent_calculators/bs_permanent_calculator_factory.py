@@ -5,7 +5,6 @@ Same names, enum values, defaults and fallback as the reference
 default type RYSER (:42), unknown types fall back to Chin-Huh (:84-86).
 """
 import enum
-from typing import Optional
 
 from .bs_permanent_calculator_interface import BSPermanentCalculatorInterface
 from .chin_huh_permanent_calculator import ChinHuhPermanentCalculator

@@ -13,7 +13,7 @@ torch is used for plumbing only (device buffers, streams, the collective).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
