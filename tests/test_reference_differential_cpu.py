@@ -158,3 +158,79 @@ def test_gccb_family_replays_the_reference_under_the_same_numpy_seed(reference, 
     np.random.seed(9)
     GeneralizedCliffordsBSimulationStrategy(RyserPermanentCalculator(U.copy()), rng_mode="numpy").simulate(s, 3)
     assert np.random.random() == after_ref
+
+
+def test_utilities_equal_the_reference_over_a_grid(reference):
+    """boson_sampling_utilities.py of the reference vs the drop-in module: state enumeration (order included), lossy input
+    states, occupation <-> assignment conversions, effective scattering matrices, the 2m-mode dilation, QFT / random-phase
+    matrices (same NumPy draws) and the state-space counting helpers."""
+    from theboss_b200.boson_sampling_utilities import boson_sampling_utilities as ours
+    ref = reference("boson_sampling_utilities.boson_sampling_utilities")
+    for n in range(0, 6):
+        for m in range(1, 6):
+            for losses in (False, True):
+                assert [tuple(x) for x in ref.generate_possible_states(n, m, losses)] == ours.generate_possible_states(n, m, losses), (n, m, losses)
+                assert ref.bosonic_space_dimension(n, m, losses) == ours.bosonic_space_dimension(n, m, losses)
+                assert ref.generate_state_types(m, n, losses) == ours.generate_state_types(m, n, losses)
+                assert ref.compute_number_of_state_types(m, n, losses) == ours.compute_number_of_state_types(m, n, losses)
+            for k in range(0, 7):
+                assert (ref.compute_number_of_k_element_integer_partitions_of_n(k, n)
+                        == ours.compute_number_of_k_element_integer_partitions_of_n(k, n))
+    rng = np.random.RandomState(5)
+    for _ in range(40):
+        m = int(rng.randint(1, 6))
+        state = [int(x) for x in rng.randint(0, 3, m)]
+        assert tuple(ref.mode_occupation_to_mode_assignment(state)) == ours.mode_occupation_to_mode_assignment(state)
+        assignment = ours.mode_occupation_to_mode_assignment(state)
+        assert tuple(ref.mode_assignment_to_mode_occupation(assignment, m)) == ours.mode_assignment_to_mode_occupation(assignment, m)
+        assert ref.compute_number_of_states_of_given_type(state) == ours.compute_number_of_states_of_given_type(state)
+        for left in range(sum(state) + 1):
+            want = [tuple(int(v) for v in x) for x in ref.generate_lossy_n_particle_input_states(state, left)]
+            assert want == ours.generate_lossy_n_particle_input_states(state, left), (state, left)
+        U = workloads.haar(m, 100 + m)
+        out_state = [int(x) for x in rng.randint(0, 3, m)]
+        want = ref.EffectiveScatteringMatrixCalculator(U, state, out_state).calculate()
+        got = ours.EffectiveScatteringMatrixCalculator(U, state, out_state).calculate()
+        assert len(want) == len(got) and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(want, got))
+        lossy = U @ np.diag(np.sqrt(rng.uniform(0.2, 1.0, m)))
+        assert np.allclose(ref.prepare_interferometer_matrix_in_expanded_space(lossy),
+                           ours.prepare_interferometer_matrix_in_expanded_space(lossy), atol=1e-13)
+        assert np.allclose(ref.get_modes_transmissivity_values_from_matrix(lossy), ours.get_modes_transmissivity_values_from_matrix(lossy))
+        k = int(rng.randint(0, m + 1))
+        assert np.allclose(ref.generate_qft_matrix_for_first_m_modes(k, m), ours.generate_qft_matrix_for_first_m_modes(k, m), atol=1e-14)
+        np.random.seed(17)
+        want = ref.generate_random_phases_matrix_for_first_m_modes(k, m)
+        after = np.random.random()
+        np.random.seed(17)
+        assert np.allclose(want, ours.generate_random_phases_matrix_for_first_m_modes(k, m), atol=1e-15)
+        assert np.random.random() == after
+
+
+def test_distribution_calculators_equal_the_reference(reference, monkeypatch):
+    """Exact distributions with fixed and with uniform losses (row f2): outcome order and every probability against the
+    reference's calculators on bunched inputs (the reference loops over single compute_permanent calls and a process pool;
+    the drop-in sends all (outcome, lossy input) pairs through one batched call)."""
+    from oracle import handle_standin
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.chin_huh_permanent_calculator import ChinHuhPermanentCalculator
+    from theboss_b200.distribution_calculators import bs_exact_distribution_with_uniform_losses as ours
+    handle_standin.install(monkeypatch)
+    ref = reference("distribution_calculators.bs_exact_distribution_with_uniform_losses")
+    ref_calc = reference(_PC + "chin_huh_permanent_calculator").ChinHuhPermanentCalculator
+
+    def config(module, U, s, lost, eta):
+        return module.BosonSamplingExperimentConfiguration(
+            interferometer_matrix=U, initial_state=list(s), initial_number_of_particles=int(sum(s)), number_of_modes=len(s),
+            number_of_particles_lost=lost, number_of_particles_left=int(sum(s)) - lost, uniform_transmissivity=eta)
+
+    for seed, s, lost, eta in ((31, [2, 1, 0, 1], 0, 1.0), (32, [2, 1, 0, 1], 2, 0.7), (33, [1, 1, 1], 1, 0.4), (34, [0, 3, 0, 0, 1], 3, 0.9)):
+        U = workloads.haar(len(s), seed)
+        for name in ("BSDistributionCalculatorWithFixedLosses", "BSDistributionCalculatorWithUniformLosses"):
+            want_calc = getattr(ref, name)(config(ref, U, s, lost, eta), ref_calc(U.copy(), None, None))
+            got_calc = getattr(ours, name)(config(ours, U, s, lost, eta), ChinHuhPermanentCalculator(U.copy()))
+            assert [tuple(o) for o in want_calc.get_outcomes_in_proper_order()] == [tuple(o) for o in got_calc.get_outcomes_in_proper_order()]
+            want, got = want_calc.calculate_distribution(), got_calc.calculate_distribution()
+            assert type(got) is list and len(got) == len(want)
+            assert np.allclose(got, want, rtol=1e-10, atol=1e-14), (name, s, lost, eta)
+            some = [tuple(o) for o in got_calc.get_outcomes_in_proper_order()][::3]
+            assert np.allclose(got_calc.calculate_probabilities_of_outcomes(some), want_calc.calculate_probabilities_of_outcomes(some),
+                               rtol=1e-10, atol=1e-14)
