@@ -234,3 +234,36 @@ def test_distribution_calculators_equal_the_reference(reference, monkeypatch):
             some = [tuple(o) for o in got_calc.get_outcomes_in_proper_order()][::3]
             assert np.allclose(got_calc.calculate_probabilities_of_outcomes(some), want_calc.calculate_probabilities_of_outcomes(some),
                                rtol=1e-10, atol=1e-14)
+
+
+def test_gcc_version_a_replays_the_reference_under_the_same_seeds(reference, monkeypatch):
+    """GeneralizedCliffordsSimulationStrategy (row a11) and its uniform-loss subclass (row f3) on further inputs than the
+    committed fixtures: same NumPy / stdlib seeds -> same samples, same memoised pmf layers."""
+    import random
+    from oracle import handle_standin
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.chin_huh_permanent_calculator import ChinHuhPermanentCalculator
+    from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy
+    from theboss_b200.simulation_strategies.generalized_cliffords_uniform_losses_simulation_strategy import (
+        GeneralizedCliffordsUniformLossesSimulationStrategy)
+    handle_standin.install(monkeypatch)
+    ref_calc = reference(_PC + "chin_huh_permanent_calculator").ChinHuhPermanentCalculator
+    ref_a = reference("simulation_strategies.generalized_cliffords_simulation_strategy").GeneralizedCliffordsSimulationStrategy
+    ref_au = reference("simulation_strategies.generalized_cliffords_uniform_losses_simulation_strategy").GeneralizedCliffordsUniformLossesSimulationStrategy
+    for seed, s in ((1, [1, 1, 1, 0, 0]), (2, [0, 4, 0, 0]), (3, [1, 0, 0]), (4, [2, 2, 0, 1, 0, 0])):
+        U = workloads.haar(len(s), 40 + seed)
+        want_strategy, got_strategy = ref_a(ref_calc(U.copy(), None, None)), GeneralizedCliffordsSimulationStrategy(ChinHuhPermanentCalculator(U.copy()))
+        np.random.seed(seed)
+        want = want_strategy.simulate(list(s), 60)
+        np.random.seed(seed)
+        got = got_strategy.simulate(list(s), 60)
+        assert [tuple(int(v) for v in x) for x in got] == [tuple(int(v) for v in x) for x in want], s
+        assert type(got) is type(want) and type(got[0]) is type(want[0])
+        for key, pmf in want_strategy.pmfs.items():
+            assert np.allclose(got_strategy.pmfs[tuple(key)], pmf, rtol=1e-10, atol=1e-14), (s, key)
+        want_strategy, got_strategy = ref_au(ref_calc(U.copy(), None, None), 0.7), GeneralizedCliffordsUniformLossesSimulationStrategy(ChinHuhPermanentCalculator(U.copy()), 0.7)
+        random.seed(seed), np.random.seed(seed)
+        want = want_strategy.simulate(list(s), 60)
+        random.seed(seed), np.random.seed(seed)
+        got = got_strategy.simulate(list(s), 60)
+        assert np.array_equal(np.array(got), np.array(want)), s
+        assert np.allclose(got_strategy.distribution, want_strategy.distribution, rtol=1e-10, atol=1e-14)
