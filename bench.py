@@ -313,7 +313,57 @@ def secondary_metrics(device):
     return out
 
 
-def gccb_sampling_leg(world, rank, local_rank, per_rank=4096):
+def sampling_algorithmic_flops(samples, seed=0):
+    """Algorithmic flops of the GCC-B runs that produced `samples` ((S, m) output occupations, n particles each):
+    sum over samples and steps k = 2 .. n of T_k * (22 k - 36), T_k = ceil(prod_j (t_j + 1) / 2) for the occupation t of
+    the k - 1 outputs drawn before step k (the count of the Glynn / Lemma-2 form the
+    kernels evaluate, NOT the reference's 4x larger sub-Ryser sweep).  The order in which a sample's particles were drawn is
+    not kept, but the chain-rule sequence of output modes is exchangeable (its joint pmf is |perm|^2 up to symmetric
+    factors, invariant under permutations of the sequence), so given the final occupation every order is equally likely:
+    one uniformly random order per sample gives an unbiased figure whose relative spread over thousands of samples is
+    far below a percent (tests/test_host_logic.py checks it against the true draw order of the oracle's loop)."""
+    samples = np.asarray(samples, dtype=np.int64)
+    S, m = samples.shape
+    n = int(samples[0].sum()) if S else 0
+    if S == 0 or n < 2:
+        return 0.0
+    if not (samples.sum(axis=1) == n).all():
+        raise ValueError("samples hold different particle numbers")
+    rng = np.random.RandomState(seed)
+    modes = np.repeat(np.tile(np.arange(m), S), samples.reshape(-1)).reshape(S, n)       # particle list of every sample
+    order = np.argsort(rng.random_sample((S, n)), axis=1)
+    modes = np.take_along_axis(modes, order, axis=1)                                     # uniformly random draw order
+    occupation = np.zeros((S, m), dtype=np.int64)
+    rows = np.arange(S)
+    flops = 0.0
+    for k in range(2, n + 1):
+        occupation[rows, modes[:, k - 2]] += 1                                           # outputs drawn before step k
+        terms = (np.prod(occupation + 1, axis=1, dtype=np.float64) + 1) // 2
+        flops += float(terms.sum()) * (22 * k - 36)
+    return flops
+
+
+def sampling_roofline(samples, ms, fp64_peak, world):
+    """`roofline` object of the GCC-B sampling leg: algorithmic flops of the run (from its own outputs) per second of
+    device time, against the FP64 probe of rank 0 times the number of ranks."""
+    try:
+        total, n = int(samples.shape[0]), int(samples[0].sum())
+        flops = sampling_algorithmic_flops(samples)
+        achieved = flops / (ms * 1e-3) / 1e12
+        return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak * world, "unit": "TFLOP/s",
+                "frac": achieved / (fp64_peak * world), "traffic": None,
+                "kernel": "k3_minors_kernel (the finish / init / tape kernels and the copies of the timed call are inside the time)",
+                "algorithmic_flops": flops, "mean_flops_per_sample": flops / total,
+                "collision_free_flops_per_sample": float(sum(2.0 ** (k - 2) * (22 * k - 36) for k in range(2, n + 1))),
+                "structural_ceiling": (22 * n - 36) / (2 * 14.0 * n),
+                "note": "flops = sum over samples and steps of ceil(prod(t_j + 1) / 2) * (22 k - 36) on the run's own outputs "
+                        "(sampling_algorithmic_flops); ceiling = useful flops per term / (2 x ~14 k FP64 instructions per term) "
+                        "at k = n; peak = rank 0's FP64 probe x ranks"}
+    except Exception as e:   # noqa: BLE001 -- the samples/s figure must survive a failure of the flop accounting
+        return {"error": repr(e)}
+
+
+def gccb_sampling_leg(world, rank, local_rank, fp64_peak, per_rank=4096):
     """Second half of the headline metric: GCC-B samples/s at n=24, m=48 (BASELINE configs[2] as a whole
     sampling run).  Weak scaling: every rank draws `per_rank` samples of one job of per_rank * world samples
     (contiguous slices, Philox keyed by the global sample index, no traffic until the final gather).  Timed on
@@ -351,9 +401,10 @@ def gccb_sampling_leg(world, rank, local_rank, per_rank=4096):
     everything = gather_samples(torch.from_numpy(local).to(f"cuda:{local_rank}")).cpu().numpy()
     gather_s = time.perf_counter() - t0
     ok = everything.shape == (total, m) and bool((everything.sum(axis=1) == n).all())
+    roofline = sampling_roofline(everything, best_ms, fp64_peak, world)
     return {"metric": "gcc_samples_per_s_n24_m48", "value": total / (best_ms * 1e-3), "unit": "samples/s", "samples": total,
             "samples_per_rank": per_rank, "scaling": "weak", "ms": best_ms, "gpu_launches": int(launches),
-            "final_gather_s": gather_s, "particles_conserved": ok,
+            "final_gather_s": gather_s, "particles_conserved": ok, "roofline": roofline,
             "note": "GeneralizedCliffordsBSimulationStrategy loop (K3 minors + finish kernel per step) on Haar(48, seed 24), "
                     "input |1^24 0^24>; device time incl. H2D of U and D2H of the samples, max over ranks"}
 
@@ -475,7 +526,7 @@ def run_native(args):
     e2e_ms = float(e2e_ms.item())
     assert result_e2e == result or abs(result_e2e - result) <= 1e-13 * abs(result)
 
-    sampling = gccb_sampling_leg(world, rank, local_rank)
+    sampling = gccb_sampling_leg(world, rank, local_rank, fp64_peak)
 
     if rank == 0:
         # correctness gate on the timed result: long-double fixture of the same workload

@@ -315,3 +315,33 @@ def test_strategy_factory_defaults_and_out_of_scope_members():
     if "theboss" not in sys.modules and not any(os.path.isdir(os.path.join(p, "theboss")) for p in sys.path if p):
         with pytest.raises(NotImplementedError, match="FixedLossSimulationStrategy"):
             factory.generate_strategy()
+
+
+def test_bench_flop_accounting_of_a_sampling_run_matches_the_true_draw_order():
+    """bench.py -> gcc_sampling.roofline counts the algorithmic flops of a GCC-B run from its output samples alone, using
+    the exchangeability of the chain-rule sequence (a uniformly random draw order per sample).  Check against the TRUE
+    draw order, recorded from the oracle's sampling loop: same total within the statistical spread, and the estimator
+    is exact on collision-free outputs."""
+    import bench
+    from oracle import pyoracle as orc
+    from tests import workloads
+    n, m, S = 6, 9, 1500
+    U = workloads.haar(m, 77)
+    s = np.array([1] * n + [0] * (m - n), dtype=np.int32)
+    rng = np.random.RandomState(8)
+    true_flops, samples = 0.0, np.zeros((S, m), dtype=np.int64)
+    for i in range(S):
+        cur, r, remaining = np.zeros(m, dtype=np.int32), np.zeros(m, dtype=np.int32), orc.mode_assignment(s)
+        for k in range(1, n + 1):                                   # the loop of orc.gccb_simulate, keeping the order
+            if k >= 2:
+                true_flops += float((np.prod(r + 1) + 1) // 2) * (22 * k - 36)
+            cur[remaining.pop(int(rng.random_sample() * len(remaining)))] += 1
+            r[orc.numpy_choice(orc.gccb_pmf(U, cur, r), rng.random_sample())] += 1
+        samples[i] = r
+    estimate = bench.sampling_algorithmic_flops(samples, seed=1)
+    assert abs(estimate - true_flops) <= 0.02 * true_flops, (estimate, true_flops)
+    assert abs(bench.sampling_algorithmic_flops(samples, seed=2) - estimate) <= 0.02 * estimate      # spread between orders
+    free = np.zeros((4, m), dtype=np.int64)
+    free[:, :n] = 1
+    assert bench.sampling_algorithmic_flops(free) == 4 * sum(2.0 ** (k - 2) * (22 * k - 36) for k in range(2, n + 1))
+    assert bench.sampling_algorithmic_flops(np.zeros((0, m))) == 0.0
