@@ -38,10 +38,17 @@ for info in pkgutil.walk_packages(theboss_b200.__path__, "theboss_b200."):
     setattr(parent, rel.rsplit(".", 1)[-1], module)
     ALIASED.append(rel)
 
-_HANDLE = oracle_handle.OracleHandle()
-_native.default_handle = lambda device=0: _HANDLE
+# BOSSPERM_SUITE_HANDLE=cuda: keep the real handle (a machine that has both the reference checkout and a B200 then runs the
+# reference's suite against the kernels themselves); default: the CPU stand-in.
+_HANDLE = None
+if os.environ.get("BOSSPERM_SUITE_HANDLE", "oracle") != "cuda":
+    _HANDLE = oracle_handle.OracleHandle()
+    _native.default_handle = lambda device=0: _HANDLE
 
 
 def pytest_terminal_summary(terminalreporter):
     terminalreporter.write_line(f"theboss -> theboss_b200 for {len(ALIASED)} modules: " + ", ".join(sorted(ALIASED)))
-    terminalreporter.write_line(f"oracle-backed handle served {_HANDLE.calls} calls from the drop-in package")
+    if _HANDLE is not None:
+        terminalreporter.write_line(f"oracle-backed handle served {_HANDLE.calls} calls from the drop-in package")
+    else:
+        terminalreporter.write_line(f"CUDA handle launched {_native.default_handle(0).launch_count()} kernels for the drop-in package")
