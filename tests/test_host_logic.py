@@ -345,3 +345,66 @@ def test_bench_flop_accounting_of_a_sampling_run_matches_the_true_draw_order():
     free[:, :n] = 1
     assert bench.sampling_algorithmic_flops(free) == 4 * sum(2.0 ** (k - 2) * (22 * k - 36) for k in range(2, n + 1))
     assert bench.sampling_algorithmic_flops(np.zeros((0, m))) == 0.0
+
+
+def test_bobs_per_sample_matrices_and_slicing(monkeypatch):
+    """What the two BOBS strategies hand to bp_gccb_simulate_batch: every per-sample matrix must be what the reference
+    builds -- M0 @ diag(phases) @ QFT in the top-left block of an isometric 2m-mode dilation
+    (nonuniform_losses_approximation_strategy.py:331-347), resp. a column-permuted unitary times phases times QFT
+    (lossy_state_approximated_simulation_strategy.py:329-362) -- although only the columns that change are recomputed per
+    sample; requests are cut into slices that continue one Philox sample counter."""
+    from tests import workloads
+    from theboss_b200 import _native
+    from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import generate_qft_matrix_for_first_m_modes
+    from theboss_b200.simulation_strategies.lossy_state_approximated_simulation_strategy import (
+        LossyStateApproximationSimulationStrategy)
+    from theboss_b200.simulation_strategies.nonuniform_losses_approximation_strategy import (
+        NonuniformLossesApproximationStrategy)
+    calls = []
+
+    class Capture:
+        def gccb_simulate_batch(self, Us, states, seed=0, first_sample=0, tape=None):
+            calls.append((np.array(Us), np.array(states), seed, first_sample))
+            return np.array(states, dtype=np.int32)          # echo: lets the test see which rows came from which slice
+
+    monkeypatch.setattr(_native, "default_handle", lambda device=0: Capture())
+
+    class Calc:
+        def __init__(self, U, s):
+            self.matrix, self.input_state = U, list(s)
+
+    m, s = 6, [2, 1, 0, 1, 1, 0]
+    lossy = workloads.haar(m, 91) @ np.diag(np.sqrt([0.5, 0.9, 0.7, 0.6, 0.8, 0.95]))
+    for k in (0, 2, 6):
+        calls.clear()
+        strat = NonuniformLossesApproximationStrategy(Calc(lossy.copy(), s), k)
+        monkeypatch.setattr(strat, "_SLICE_BYTES", 16 * 4 * m * m * 8)              # 8 samples per slice
+        np.random.seed(k)
+        out = strat.simulate(s, 20)
+        assert [c[0].shape[0] for c in calls] == [8, 8, 4] and [c[3] for c in calls] == [0, 8, 16]
+        assert len({c[2] for c in calls}) == 1                                       # one seed for the whole request
+        Us, states = np.concatenate([c[0] for c in calls]), np.concatenate([c[1] for c in calls])
+        assert np.array_equal(np.array(out), states[:, :m])
+        qft = generate_qft_matrix_for_first_m_modes(k, m)
+        for U2, st in zip(Us, states):
+            # isometry on the physical inputs, and the physical block is M0 @ (unit-modulus diagonal) @ QFT
+            assert np.abs(U2[:, :m].conj().T @ U2[:, :m] - np.eye(m)).max() < 1e-12
+            D = np.linalg.solve(strat._initial_matrix, U2[:m, :m] @ qft.conj().T)
+            assert np.abs(D - np.diag(np.diag(D))).max() < 1e-10 and np.allclose(np.abs(np.diag(D)), 1.0)
+            assert np.allclose(np.diag(D)[k:], 1.0)
+            assert st[m:].sum() == 0 and np.all(st[k:m] <= np.array(s[k:])) and st[:k].sum() <= sum(s[:k])
+            assert (st[:k] > 0).sum() <= 1                                           # approximated particles sit in one mode
+    U = workloads.haar(m, 92)
+    for hl in (0, 2, 6):
+        calls.clear()
+        strat = LossyStateApproximationSimulationStrategy(Calc(U.copy(), s), 0.6, hl)
+        monkeypatch.setattr(strat, "_SLICE_BYTES", 16 * m * m * 8)
+        np.random.seed(hl)
+        strat.simulate(s, 20)
+        assert [c[0].shape[0] for c in calls] == [8, 8, 4] and [c[3] for c in calls] == [0, 8, 16]
+        qft = generate_qft_matrix_for_first_m_modes(m - hl, m)
+        for U2, st in zip(np.concatenate([c[0] for c in calls]), np.concatenate([c[1] for c in calls])):
+            assert np.abs(U2 @ U2.conj().T - np.eye(m)).max() < 1e-12
+            P = U.conj().T @ U2 @ qft.conj().T                                       # = permutation x unit-modulus diagonal
+            assert np.allclose(np.sort(np.abs(P), axis=0)[-1], 1.0) and np.allclose(np.abs(P).sum(axis=0), 1.0, atol=1e-10)
+            assert np.all(st[:hl] <= np.array(s[:hl])) and st[hl + 1:].sum() == 0

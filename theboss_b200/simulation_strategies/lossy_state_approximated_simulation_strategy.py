@@ -6,8 +6,8 @@ reference draws a lossy input state -- the first ``hierarchy_level`` modes keep 
 eta (:96-138, :312-327), the remaining (approximated) modes are replaced by l ~ Binomial(n_approx, eta)
 particles in the first approximated mode (:170-203) -- and a matrix ``U[:, random permutation] @ random_phases @
 QFT`` acting on the approximated modes (:329-362), then takes ONE lossless GCC-B sample in a spawn process pool
-(:287-310).  Here the per-sample inputs and matrices are built vectorised on the host and all samples go through
-one batched device call (``bp_gccb_simulate_batch``).
+(:287-310).  Here the per-sample inputs and matrices are built vectorised on the host and go through batched device
+calls (``bp_gccb_simulate_batch``), one per slice of at most 256 MiB of matrices.
 
 Deviation: the not-approximated part is thinned particle by particle (Binomial(s_i, eta) per mode), which equals
 the reference's weights for collision-free inputs and stays normalised for bunched ones (the reference's weights
@@ -31,24 +31,33 @@ class LossyStateApproximationSimulationStrategy(SimulationStrategyInterface):
         self._threads_number = threads_number                     # signature parity; the GPU batches instead
         self._device = getattr(bs_permanent_calculator, "device", 0)
 
+    #: host memory bound of one device request (bytes of per-sample matrices built and shipped at a time)
+    _SLICE_BYTES = 256 << 20
+
     def simulate(self, input_state: Sequence[int], samples_number: int = 1) -> List[Tuple[int, ...]]:
         if samples_number < 1:
             return []
         U = _native.as_matrix(self._permanent_calculator.matrix)
-        m, S, eta = U.shape[0], int(samples_number), self._uniform_transmissivity
+        m, total, eta = U.shape[0], int(samples_number), self._uniform_transmissivity
         hl = min(max(self._hierarchy_level, 0), m)
         state = np.array(input_state, dtype=np.int64)
-        states = np.zeros((S, m), dtype=np.int32)
-        states[:, :hl] = np.random.binomial(np.repeat(state[None, :hl], S, axis=0), eta)
-        if hl < m:
-            states[:, hl] = np.random.binomial(int(state[hl:].sum()), eta, S)
-        qft = generate_qft_matrix_for_first_m_modes(m - hl, m)
-        # NOTE: like the reference (:345-362, :39-58) the random phases and the QFT act on the FIRST m - hl modes
-        phases = np.ones((S, m), dtype=np.complex128)
-        phases[:, : m - hl] = np.exp(2j * np.pi * np.random.rand(S, m - hl))
-        perms = np.argsort(np.random.rand(S, m), axis=1)                          # one column permutation per sample
-        Us = np.take_along_axis(np.repeat(U[None, :, :], S, axis=0), perms[:, None, :], axis=2)
-        Us = (Us * phases[:, None, :]) @ qft
+        # NOTE: like the reference (:345-362, :39-58) the random phases and the QFT act on the FIRST a = m - hl modes
+        a = m - hl
+        qft_a = generate_qft_matrix_for_first_m_modes(a, m)[:a, :a]
         seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
-        out = _native.default_handle(self._device).gccb_simulate_batch(np.ascontiguousarray(Us), states, seed=seed)
+        handle = _native.default_handle(self._device)
+        step = max(1, min(total, self._SLICE_BYTES // (16 * m * m)))
+        out = np.zeros((total, m), dtype=np.int32)
+        for lo in range(0, total, step):
+            S = min(step, total - lo)
+            states = np.zeros((S, m), dtype=np.int32)
+            states[:, :hl] = np.random.binomial(np.repeat(state[None, :hl], S, axis=0), eta)
+            if hl < m:
+                states[:, hl] = np.random.binomial(int(state[hl:].sum()), eta, S)
+            phases = np.exp(2j * np.pi * np.random.rand(S, a))
+            perms = np.argsort(np.random.rand(S, m), axis=1)                      # one column permutation per sample
+            Us = np.ascontiguousarray(np.transpose(U.T[perms], (0, 2, 1)))        # Us[s] = U[:, perms[s]]
+            if a > 0:                                                             # only the first a columns meet the phases and the QFT
+                Us[:, :, :a] = (Us[:, :, :a] * phases[:, None, :]) @ qft_a
+            out[lo:lo + S] = handle.gccb_simulate_batch(Us, states, seed=seed, first_sample=lo)
         return [tuple(row) for row in out.tolist()]

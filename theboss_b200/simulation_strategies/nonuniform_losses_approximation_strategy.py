@@ -6,11 +6,13 @@ reference (i) moves all particles of the approximated modes into one random appr
 (ii) thins the input by the uniform loss extracted from the matrix (:298-329), (iii) builds a fresh matrix
 ``M0 @ random_phases @ QFT`` (:331-347) and (iv) takes ONE sample of the lossy-network GCC-B sampler on its
 2m x 2m dilation, all inside a spawn process pool (:254-257).  Here (i)-(iii) are vectorised NumPy on the host and
-(iv) is one batched device call with a matrix and an input state per sample (``bp_gccb_simulate_batch``).
+(iv) is a batched device call with a matrix and an input state per sample (``bp_gccb_simulate_batch``), issued per slice
+of at most 256 MiB of matrices so that host memory stays bounded for any ``samples_number``.
 
 The dilation needs no per-sample SVD: with ``M0 = u diag(sv) v`` the per-sample matrix is
 ``u diag(sv) (v W)`` for the unitary ``W = phases @ QFT``, so its dilation is
-``[[M, u L], [L v W, diag(sv)]]`` with ``L = diag(sqrt(1 - sv^2))``.  (NumPy's SVD of ``M`` may differ from
+``[[M, u L], [L v W, diag(sv)]]`` with ``L = diag(sqrt(1 - sv^2))``; and because the phases and the QFT only act on
+the k approximated modes, only the first k columns of ``M`` and ``L v W`` change from sample to sample.  (NumPy's SVD of ``M`` may differ from
 this one by phases on the loss modes, which are traced out; output statistics are identical.)
 
 Deviations: exactly ``samples_number`` samples are returned (the reference rounds up to a multiple of its thread
@@ -45,32 +47,44 @@ class NonuniformLossesApproximationStrategy:
         self._svd = (u, np.clip(sv, 0.0, 1.0), v)
         self._initial_matrix = u @ np.diag(sv) @ v
 
+    #: host memory bound of one device request: per-sample matrices are built and shipped in slices of at most this many bytes
+    _SLICE_BYTES = 256 << 20
+
     def simulate(self, input_state: Sequence[int], samples_number: int = 1) -> List[Tuple[int, ...]]:
         if samples_number < 1:
             return []
-        m, k, S = len(input_state), self._approximated_modes_number, int(samples_number)
+        m, k, total = len(input_state), self._approximated_modes_number, int(samples_number)
         base = np.array(input_state, dtype=np.int64)
         approx_particles = int(base[:k].sum())
         base[:k] = 0
-        states = np.repeat(base[None, :], S, axis=0)
-        if k > 0:
-            states[np.arange(S), np.random.randint(0, k, S)] = approx_particles
-        if not np.isclose(self._uniform_losses, 0):
-            states = np.random.binomial(states, 1.0 - self._uniform_losses)     # each particle survives independently
-        # per-sample matrices: M_s = M0 @ diag(phases_s) @ QFT, dilated to 2m modes
+        # Only the first k columns of M_s = M0 @ diag(phases_s) @ QFT and of its loss block L v W_s depend on the sample
+        # (the QFT and the phases act on the approximated modes): stack B = [[M0], [L v]] (2m x m) once, then per sample
+        # B[:, :k] diag(phases_s) QFT_k -- 2 m k^2 multiplications instead of two m^3 products.
         u, sv, v = self._svd
-        qft = generate_qft_matrix_for_first_m_modes(k, m)
-        phases = np.ones((S, m), dtype=np.complex128)
-        phases[:, :k] = np.exp(2j * np.pi * np.random.rand(S, k))
-        vW = (v[None, :, :] * phases[:, None, :]) @ qft                         # (S, m, m)
         loss = np.sqrt(np.clip(1.0 - sv ** 2, 0.0, None))
-        Us = np.zeros((S, 2 * m, 2 * m), dtype=np.complex128)
-        Us[:, :m, :m] = (u * sv[None, :]) @ vW
-        Us[:, m:, :m] = loss[None, :, None] * vW
-        Us[:, :m, m:] = (u * loss[None, :])[None, :, :]
-        Us[:, m:, m:] = np.diag(sv)[None, :, :]
-        big_states = np.zeros((S, 2 * m), dtype=np.int32)
-        big_states[:, :m] = states
+        stacked = np.concatenate([(u * sv[None, :]) @ v, loss[:, None] * v], axis=0)
+        template = np.zeros((2 * m, 2 * m), dtype=np.complex128)
+        template[:, k:m] = stacked[:, k:]
+        template[:m, m:] = u * loss[None, :]
+        template[m:, m:] = np.diag(sv)
+        qft_k = generate_qft_matrix_for_first_m_modes(k, m)[:k, :k]
         seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
-        out = _native.default_handle(self._device).gccb_simulate_batch(Us, big_states, seed=seed)
-        return [tuple(row) for row in out[:, :m].tolist()]
+        handle = _native.default_handle(self._device)
+        step = max(1, min(total, self._SLICE_BYTES // (16 * 4 * m * m)))
+        out = np.zeros((total, m), dtype=np.int32)
+        for lo in range(0, total, step):
+            S = min(step, total - lo)
+            states = np.repeat(base[None, :], S, axis=0)
+            if k > 0:
+                states[np.arange(S), np.random.randint(0, k, S)] = approx_particles
+            if not np.isclose(self._uniform_losses, 0):
+                states = np.random.binomial(states, 1.0 - self._uniform_losses)     # each particle survives independently
+            Us = np.repeat(template[None, :, :], S, axis=0)
+            if k > 0:
+                phases = np.exp(2j * np.pi * np.random.rand(S, k))
+                Us[:, :, :k] = (stacked[None, :, :k] * phases[:, None, :]) @ qft_k
+            big_states = np.zeros((S, 2 * m), dtype=np.int32)
+            big_states[:, :m] = states
+            # one Philox stream for the whole request: slices continue the sample counter
+            out[lo:lo + S] = handle.gccb_simulate_batch(Us, big_states, seed=seed, first_sample=lo)[:, :m]
+        return [tuple(row) for row in out.tolist()]
