@@ -26,6 +26,16 @@ def _state(x, m: int) -> np.ndarray:
     return out
 
 
+def _keyed_tape(seed, first_sample, n_samples: int, width: int) -> np.ndarray:
+    """Uniforms keyed by (seed, global sample index) like the device's counter-based generator, so that results do not
+    depend on how a job is cut into calls (different numbers than Philox, same distribution)."""
+    tape = np.zeros((n_samples, width))
+    for i in range(n_samples):
+        key = (int(seed) * 0x9E3779B1 + int(first_sample) + i) % 2 ** 32
+        tape[i] = np.random.RandomState(key).random_sample(width)
+    return tape
+
+
 class OracleHandle:
     device = 0
 
@@ -38,6 +48,12 @@ class OracleHandle:
         self.calls += 1
         A = _matrix(A)
         return complex(1) if A.shape[0] == 0 else orc.glynn_matrix(A, self._precision)
+
+    def glynn_matrix_range(self, A, lo, hi):
+        """Un-normalised partial over Gray steps [lo, hi) as (re_hi, re_lo, im_hi, im_lo)."""
+        self.calls += 1
+        part = orc.glynn_range(_matrix(A), int(lo), int(hi), "ld") if hi > lo else 0j
+        return (part.real, 0.0, part.imag, 0.0)
 
     def glynn_single(self, U, s, t):
         self.calls += 1
@@ -77,14 +93,13 @@ class OracleHandle:
 
     # -- K3 + K4 -------------------------------------------------------------------------------------
     def gccb_simulate(self, U, s, n_samples, eta=-1.0, seed=0, first_sample=0, tape=None):
-        """Decisions from the given tape, else from a NumPy generator keyed by the seed (the device uses Philox: same
-        distribution, different stream)."""
+        """Decisions from the given tape, else from uniforms keyed by (seed, sample index)."""
         self.calls += 1
         U = _matrix(U)
         s = _state(s, U.shape[0])
         n = int(s.sum())
         if tape is None:
-            tape = np.random.RandomState((int(seed) + int(first_sample)) % 2 ** 32).random_sample((int(n_samples), 1 + 2 * n))
+            tape = _keyed_tape(seed, first_sample, int(n_samples), 1 + 2 * n)
         if n == 0 or n_samples == 0:
             return np.zeros((int(n_samples), U.shape[0]), dtype=np.int32)
         if eta >= 0:
@@ -97,12 +112,13 @@ class OracleHandle:
         """One GCC-B sample per (matrix, input state) pair through the oracle's sampling loop."""
         self.calls += 1
         states = np.asarray(states)
-        rng = np.random.RandomState(int(seed) % 2 ** 32)
         out = np.zeros(states.shape, dtype=np.int32)
+        if tape is None:
+            tape = _keyed_tape(seed, first_sample, states.shape[0], 1 + 2 * int(states.sum(axis=1).max(initial=0)))
         for i in range(states.shape[0]):
             n = int(states[i].sum())
             if n:
-                row = rng.random_sample((1, 1 + 2 * n)) if tape is None else tape[i:i + 1, : 1 + 2 * n]
+                row = tape[i:i + 1, : 1 + 2 * n]
                 out[i] = orc.gccb_simulate(Us[i], states[i], row, precision=self._precision)[0]
         return out
 
