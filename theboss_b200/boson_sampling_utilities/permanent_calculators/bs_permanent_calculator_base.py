@@ -83,3 +83,8 @@ class BSPermanentCalculatorBase(BSPermanentCalculatorInterface):
             raise AttributeError("input and output states hold different particle numbers")
         out = self._handle().perm_batched(U, s[None, :].astype(np.uint8), t[None, :].astype(np.uint8), self._formula)
         return np.complex128(out[0])
+
+
+# The reference derives Ryser / Chin-Huh from a second base that adds the Guan-code driver
+# (bs_permanent_calculator_base.py:75-209); the walk lives in kernel K2 here, so both names denote the same class.
+BSGuanCodeBasedPermanentCalculatorBase = BSPermanentCalculatorBase
