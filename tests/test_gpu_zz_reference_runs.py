@@ -38,3 +38,34 @@ def test_version_a_uniform_losses_sampler_reproduces_reference_samples(golden_di
     and NumPy generators give the reference's samples bit for bit, with the layer permanents from kernel K2."""
     from tests.test_host_logic import _check_uniform_losses_a_fixture
     _check_uniform_losses_a_fixture(golden_dir)
+
+
+def test_kernels_against_reference_outputs_on_config_2_and_3_workloads(golden_dir):
+    """tests/golden/reference_large.json (the unmodified reference on BASELINE config 2 items at n = 20 and config 3 steps at
+    k = 12 .. 16, tests/golden/make_reference_large_golden.py): the drop-in classes, i.e. kernels K1 / K2 / K3, within
+    BASELINE's relative tolerance of 1e-10 of the reference's own outputs (whose float64 error is up to 6.5e-11 here)."""
+    import json
+    import os
+    from tests import workloads
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.bs_cc_ch_submatrices_permanent_calculator import (
+        BSCCCHSubmatricesPermanentCalculator)
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.bs_cc_ryser_submatrices_permanent_calculator import (
+        BSCCRyserSubmatricesPermanentCalculator)
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.chin_huh_permanent_calculator import ChinHuhPermanentCalculator
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.glynn_gray_permanent_calculator import GlynnGrayPermanentCalculator
+    with open(os.path.join(golden_dir, "reference_large.json")) as f:
+        g = json.load(f)
+    U, S, T = workloads.c2_batch(g["c2"]["n"], g["c2"]["m"], g["c2"]["items"])
+    for which, cls in (("chin_huh", ChinHuhPermanentCalculator), ("glynn", GlynnGrayPermanentCalculator)):
+        for i, (re, im) in g["c2"][which].items():
+            want = complex(re, im)
+            got = cls(U, [int(x) for x in S[int(i)]], [int(x) for x in T[int(i)]]).compute_permanent()
+            assert abs(got - want) <= 1e-10 * abs(want), (which, i, got, want)
+    for key, values in g["c3"].items():
+        k, free = int(key[1:key.index("_")]), key.endswith("free")
+        U3, s, t = workloads.c3_step(k, 2 * k, collision_free=free)
+        for which, v in values.items():
+            cls = BSCCRyserSubmatricesPermanentCalculator if which == "ryser" else BSCCCHSubmatricesPermanentCalculator
+            want = np.array([complex(*x) for x in v])
+            got = np.array(cls(U3, [int(x) for x in s], [int(x) for x in t]).compute_permanents())
+            assert got.shape == want.shape and np.abs(got - want).max() <= 1e-10 * np.abs(want).max(), (key, which)

@@ -178,3 +178,33 @@ def test_reference_outputs_at_n14_to_n20_pin_the_oracle_and_the_large_ground_tru
     with open(os.path.join(golden_dir, "large_permanents.json")) as f:
         big = json.load(f)["glynn_n20"]
     assert _rel(complex(big["re"], big["im"]), complex(ref["20"]["re"], ref["20"]["im"])) <= 1e-10
+
+
+def test_reference_outputs_on_config_2_and_3_workloads_pin_the_oracle(golden_dir):
+    """tests/golden/reference_large.json: the unmodified reference on BASELINE config 2 items (n = 20, m = 40, repeated rows
+    and columns; Chin-Huh and Glynn calculators) and config 3 steps (all minors at k = 12 .. 16, sub-Ryser and sub-Chin-Huh).
+    The oracle's double variant follows the reference's operation order and reproduces these values to the last bit; the
+    80-bit variant differs by the reference's own float64 error (up to 6.5e-11 on these items)."""
+    from tests import workloads
+    with open(os.path.join(golden_dir, "reference_large.json")) as f:
+        g = json.load(f)
+    U, S, T = workloads.c2_batch(g["c2"]["n"], g["c2"]["m"], g["c2"]["items"])
+    worst = 0.0
+    for which in ("chin_huh", "glynn"):
+        assert len(g["c2"][which]) == g["c2"]["items"]
+        for i, (re, im) in g["c2"][which].items():
+            s, t, want = S[int(i)].astype(np.int32), T[int(i)].astype(np.int32), complex(re, im)
+            same_order = orc.guan_permanent(U, s, t, orc.CHIN_HUH, "d") if which == "chin_huh" else orc.glynn(U, s, t, "d")
+            assert _rel(same_order, want) <= 1e-14, (which, i)
+            worst = max(worst, _rel(orc.guan_permanent(U, s, t, orc.CHIN_HUH, "ld"), want))
+    assert worst <= 1e-10
+    assert len(g["c3"]) == 6
+    for key, values in g["c3"].items():
+        k, free = int(key[1:key.index("_")]), key.endswith("free")
+        U3, s, t = workloads.c3_step(k, 2 * k, collision_free=free)
+        truth = orc.submatrices(U3, s, t, orc.RYSER, "ld")
+        for which, v in values.items():
+            want = np.array([complex(*x) for x in v])
+            same_order = orc.submatrices(U3, s, t, orc.RYSER if which == "ryser" else orc.CHIN_HUH, "d")
+            assert np.abs(same_order - want).max() <= 1e-14 * np.abs(want).max(), (key, which)
+            assert np.abs(truth - want).max() <= 1e-10 * np.abs(want).max(), (key, which)
