@@ -69,3 +69,11 @@ def test_kernels_against_reference_outputs_on_config_2_and_3_workloads(golden_di
             want = np.array([complex(*x) for x in v])
             got = np.array(cls(U3, [int(x) for x in s], [int(x) for x in t]).compute_permanents())
             assert got.shape == want.shape and np.abs(got - want).max() <= 1e-10 * np.abs(want).max(), (key, which)
+
+
+def test_seeded_gccb_runs_reproduce_reference_samples(golden_dir):
+    """tests/golden/gccb_seeded_samples.npz: GCC-B, its uniform-loss variant and the lossy-network wrapper at n = 12 .. 16
+    (m up to 32), seeded through `numpy.random.seed` exactly like the reference run that produced the fixture; the device
+    loop (K3 minors + finish kernel per step) must return the reference's samples bit for bit."""
+    from tests.test_host_logic import _check_seeded_gccb_fixture
+    _check_seeded_gccb_fixture(golden_dir)

@@ -408,3 +408,33 @@ def test_bobs_per_sample_matrices_and_slicing(monkeypatch):
             P = U.conj().T @ U2 @ qft.conj().T                                       # = permutation x unit-modulus diagonal
             assert np.allclose(np.sort(np.abs(P), axis=0)[-1], 1.0) and np.allclose(np.abs(P).sum(axis=0), 1.0, atol=1e-10)
             assert np.all(st[:hl] <= np.array(s[:hl])) and st[hl + 1:].sum() == 0
+
+
+def _check_seeded_gccb_fixture(golden_dir):
+    """Shared by the CPU (oracle loop) and GPU (kernels K3 / K4) tests: `rng_mode="numpy"` strategies under the seeds of
+    tests/golden/make_gccb_seeded_golden.py must return the unmodified reference's samples (n = 12 .. 16) bit for bit."""
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.ryser_permanent_calculator import RyserPermanentCalculator
+    from theboss_b200.simulation_strategies.generalized_cliffords_b_simulation_strategy import GeneralizedCliffordsBSimulationStrategy
+    from theboss_b200.simulation_strategies.generalized_cliffords_b_uniform_losses_simulation_strategy import (
+        GeneralizedCliffordsBUniformLossesSimulationStrategy)
+    from theboss_b200.simulation_strategies.lossy_networks_generalized_cliffords_simulation_strategy import (
+        LossyNetworksGeneralizedCliffordsSimulationStrategy)
+    z = np.load(os.path.join(golden_dir, "gccb_seeded_samples.npz"))
+    assert len(z["names"]) == 6
+    for name in z["names"]:
+        kind, U, s, want = str(z[f"{name}_kind"]), z[f"{name}_U"], [int(x) for x in z[f"{name}_s"]], z[f"{name}_samples"]
+        calc = RyserPermanentCalculator(U.copy())
+        if kind == "plain":
+            strategy = GeneralizedCliffordsBSimulationStrategy(calc, rng_mode="numpy")
+        elif kind == "uniform":
+            strategy = GeneralizedCliffordsBUniformLossesSimulationStrategy(calc, float(z[f"{name}_eta"]), rng_mode="numpy")
+        else:
+            strategy = LossyNetworksGeneralizedCliffordsSimulationStrategy(calc, rng_mode="numpy")
+        np.random.seed(int(z[f"{name}_seed"]))
+        got = np.array([[int(v) for v in x] for x in strategy.simulate(s, want.shape[0])], dtype=np.int64)
+        assert np.array_equal(got, want), name
+
+
+def test_seeded_gccb_runs_reproduce_reference_samples_with_the_oracle_loop(golden_dir, monkeypatch):
+    _install_oracle_handle(monkeypatch)
+    _check_seeded_gccb_fixture(golden_dir)
