@@ -16,10 +16,9 @@ for r in range(reps + 1):
     out = h.gccb_simulate(U, s, S, seed=5)
     dt = time.perf_counter() - t0
     print(f"n={n} S={S}: {dt*1e3:.2f} ms, {S/dt:.1f} samples/s, launches so far {h.launch_count()}", flush=True)
-# algorithmic flops of the run: per step T * (22k - 36), T = prod(t_j + 1) / 2 over the outputs sampled so far
-tot = 0.0
-for row in out:
-    # order of arrival inside a sample is not returned; bound by the final occupation: sum over prefixes is <= 2x the last step
-    t = row.astype(np.float64)
-    tot += np.prod(t + 1) / 2
-print(f"sum over samples of the final-step walk length bound prod(t+1)/2 (with all n outputs): {tot:.3e}")
+# algorithmic flops of the run (sum over samples and steps of ceil(prod(t_j + 1) / 2) * (22 k - 36), counted on the run's own
+# outputs): compare with ncu's dadd + dmul + 2 * dfma over all k3_minors launches of ONE run (reps = 0)
+import bench
+flops = bench.sampling_algorithmic_flops(out)
+print(f"algorithmic flops of one run: {flops:.4e} ({flops / S:.4e} per sample; collision-free worst case "
+      f"{sum(2.0 ** (k - 2) * (22 * k - 36) for k in range(2, n + 1)):.4e}); useful TFLOP/s at the last timing: {flops / dt / 1e12:.2f}")
