@@ -407,9 +407,7 @@ def gccb_sampling_leg(world, rank, local_rank, fp64_peak, per_rank=4096):
         strategy = GeneralizedCliffordsBSimulationStrategy(RyserPermanentCalculator(U, device=local_rank), device=local_rank)
         np.random.seed(100 + rank)
         strategy.simulate([int(x) for x in s], 64)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()                     # (no collective inside the try: a failure on one rank must not hang the others)
         t0 = time.perf_counter()
         listed = strategy.simulate([int(x) for x in s], hi - lo)
         e2e_wall = time.perf_counter() - t0
