@@ -208,7 +208,5 @@ def test_strategy_factory_and_deepcopy():
     strat = SimulationStrategyFactory(None, calc2, StrategyType.GCC).generate_strategy()
     out = strat.simulate([1, 1, 0, 1, 0], 5)
     assert len(out) == 5 and all(sum(o) == 3 for o in out)
-    import importlib.util
-    if importlib.util.find_spec("theboss") is None:   # no reference install next to the drop-in: the mean-field members name it
-        with pytest.raises(NotImplementedError):
-            SimulationStrategyFactory(None, calc2, StrategyType.FIXED_LOSS).generate_strategy()
+    with pytest.raises(NotImplementedError):
+        SimulationStrategyFactory(None, calc2, StrategyType.FIXED_LOSS).generate_strategy()

@@ -305,16 +305,18 @@ def test_distribution_calculator_snapshots_its_configuration(monkeypatch):
 
 
 def test_strategy_factory_defaults_and_out_of_scope_members():
-    """Same default member as the reference (simulation_strategy_factory.py:52); the members that never touch a permanent
-    resolve to the reference's own classes when `theboss` is importable and raise NotImplementedError naming them when not."""
-    import sys
+    """Same default member as the reference (simulation_strategy_factory.py:52); the members that never touch a permanent are
+    not part of the drop-in and raise NotImplementedError naming the reference class (there is no CPU path in the package)."""
     from theboss_b200.simulation_strategies import simulation_strategy_factory as ssf
     factory = ssf.SimulationStrategyFactory(None, None)
     assert factory.strategy_type == ssf.StrategyType.FIXED_LOSS and factory.available_threads_number == -1
     assert [t.value for t in ssf.StrategyType] == list(range(1, 10))
-    if "theboss" not in sys.modules and not any(os.path.isdir(os.path.join(p, "theboss")) for p in sys.path if p):
-        with pytest.raises(NotImplementedError, match="FixedLossSimulationStrategy"):
+    for member, cls in ((ssf.StrategyType.FIXED_LOSS, "FixedLossSimulationStrategy"), (ssf.StrategyType.UNIFORM_LOSS, "UniformLossSimulationStrategy"),
+                        (ssf.StrategyType.CLIFFORD_R, "CliffordsRSimulationStrategy"), (ssf.StrategyType.LOSSLESS_MODES_STRATEGY, "FixedLossSimulationStrategy")):
+        factory.strategy_type = member
+        with pytest.raises(NotImplementedError, match=cls):
             factory.generate_strategy()
+
 
 
 def test_bench_flop_accounting_of_a_sampling_run_matches_the_true_draw_order():

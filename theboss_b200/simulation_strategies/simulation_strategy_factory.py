@@ -5,7 +5,7 @@ Mirrors ``StrategyType`` / ``SimulationStrategyFactory`` of the reference
 hot path.  The enum keeps every reference member (so values match), but only the GCC family is built
 here (GCC, lossy-network GCC-B, uniform-loss GCC and both BOBS variants); the mean-field and R-backed strategies
 never evaluate a permanent and are outside this package's scope (SURVEY.md section 8 marks them out of scope): for them the
-factory returns the reference's own class when ``theboss`` is importable and raises ``NotImplementedError`` naming it when not.
+factory raises ``NotImplementedError`` naming the reference class to use.
 Like the reference the factory deep-copies the calculator it is given (:58, :107, :186).
 """
 import enum
@@ -35,9 +35,8 @@ class StrategyType(enum.IntEnum):
     UNIFORM_LOSSES_BOBS = enum.auto()
 
 
-# Strategies that never evaluate a permanent (mean-field approximations, the R-backed sampler): not rebuilt here.  When
-# the reference package is installed next to this one the factory hands out the reference's own class, built exactly as
-# the reference factory builds it (:116-172); otherwise it raises NotImplementedError naming that class.
+# Members that never evaluate a permanent (mean-field approximations, the R-backed sampler) are not rebuilt here and there is
+# no CPU path in this package: the factory raises NotImplementedError naming the reference class to use instead.
 _OUT_OF_SCOPE = {
     StrategyType.FIXED_LOSS: "theboss.simulation_strategies.fixed_loss_simulation_strategy.FixedLossSimulationStrategy",
     StrategyType.UNIFORM_LOSS: "theboss.simulation_strategies.uniform_loss_simulation_strategy.UniformLossSimulationStrategy",
@@ -45,17 +44,6 @@ _OUT_OF_SCOPE = {
     # the reference maps no builder to this member and falls back to the fixed-loss strategy (:116-119)
     StrategyType.LOSSLESS_MODES_STRATEGY: "theboss.simulation_strategies.fixed_loss_simulation_strategy.FixedLossSimulationStrategy",
 }
-
-
-def _reference_class(kind: "StrategyType"):
-    import importlib
-    module_name, class_name = _OUT_OF_SCOPE[kind].rsplit(".", 1)
-    try:
-        return getattr(importlib.import_module(module_name), class_name)
-    except ImportError as error:
-        raise NotImplementedError(
-            f"{kind.name} is outside the permanent hot path built here and the reference class {_OUT_OF_SCOPE[kind]} "
-            f"cannot be imported ({error})") from error
 
 
 class SimulationStrategyFactory:
@@ -92,11 +80,6 @@ class SimulationStrategyFactory:
             return NonuniformLossesApproximationStrategy(calc, cfg.number_of_modes - cfg.hierarchy_level)
         if kind == StrategyType.UNIFORM_LOSSES_BOBS:   # :194-205
             return LossyStateApproximationSimulationStrategy(calc, cfg.uniform_transmissivity, cfg.hierarchy_level)
-        cls = _reference_class(kind if kind in _OUT_OF_SCOPE else StrategyType.FIXED_LOSS)
-        if kind == StrategyType.UNIFORM_LOSS:     # :129-139
-            return cls(cfg.interferometer_matrix, cfg.number_of_modes, cfg.uniform_transmissivity)
-        if kind == StrategyType.CLIFFORD_R:       # :141-172
-            return cls(cfg.interferometer_matrix)
-        return cls(interferometer_matrix=cfg.interferometer_matrix, number_of_photons_left=cfg.number_of_particles_left,
-                   number_of_observed_modes=cfg.number_of_modes,
-                   network_simulation_strategy=cfg.network_simulation_strategy)   # :116-127
+        raise NotImplementedError(
+            f"{kind.name} is outside the permanent hot path built here; use the reference class "
+            f"{_OUT_OF_SCOPE.get(kind, _OUT_OF_SCOPE[StrategyType.FIXED_LOSS])}")
