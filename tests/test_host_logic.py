@@ -440,3 +440,40 @@ def _check_seeded_gccb_fixture(golden_dir):
 def test_seeded_gccb_runs_reproduce_reference_samples_with_the_oracle_loop(golden_dir, monkeypatch):
     _install_oracle_handle(monkeypatch)
     _check_seeded_gccb_fixture(golden_dir)
+
+
+def test_every_entry_point_rejects_a_null_handle_without_touching_the_device():
+    """include/bossperm.h: "every function returns 0 on success or a negative bp_status; nothing throws".  With a NULL
+    handle each compute / timing entry point must come back with BP_ERR_INVALID and a message (no crash, no CUDA call),
+    which is also what a caller sees after a failed bp_create on a machine without a GPU."""
+    import ctypes as C
+    from theboss_b200 import _native
+    lib = _native.load_library()
+    out = (C.c_double * 4)()
+    A = np.eye(2, dtype=np.complex128)
+    s = np.array([1, 1], dtype=np.int32)
+    S = np.array([[1, 1]], dtype=np.uint8)
+    o, oi, pmf = np.zeros(4, dtype=np.complex128), np.zeros((1, 2), dtype=np.int32), np.zeros(2)
+    calls = {
+        "bp_synchronize": lambda: lib.bp_synchronize(None),
+        "bp_device_info": lambda: lib.bp_device_info(None, None, None, None, None),
+        "bp_timer_start": lambda: lib.bp_timer_start(None),
+        "bp_timer_stop": lambda: lib.bp_timer_stop(None, C.byref(C.c_float())),
+        "bp_fp64_peak": lambda: lib.bp_fp64_peak(None, 1.0, out),
+        "bp_glynn_matrix": lambda: lib.bp_glynn_matrix(None, A.ctypes.data, 2, out),
+        "bp_glynn_matrix_range": lambda: lib.bp_glynn_matrix_range(None, A.ctypes.data, 2, 0, 2, out),
+        "bp_glynn_matrix_range_dev": lambda: lib.bp_glynn_matrix_range_dev(None, A.ctypes.data, 2, 0, 2, None),
+        "bp_glynn_single": lambda: lib.bp_glynn_single(None, A.ctypes.data, 2, s.ctypes.data, s.ctypes.data, out),
+        "bp_perm_batched": lambda: lib.bp_perm_batched(None, A.ctypes.data, 2, S.ctypes.data, S.ctypes.data, 1, 1, o.ctypes.data),
+        "bp_perm_batched_dev": lambda: lib.bp_perm_batched_dev(None, A.ctypes.data, 2, S.ctypes.data, S.ctypes.data, 1, 1, o.ctypes.data),
+        "bp_minors": lambda: lib.bp_minors(None, A.ctypes.data, 2, s.ctypes.data, s.ctypes.data, 1, o.ctypes.data),
+        "bp_gccb_pmf": lambda: lib.bp_gccb_pmf(None, A.ctypes.data, 2, s.ctypes.data, s.ctypes.data, pmf.ctypes.data, None),
+        "bp_gccb_simulate": lambda: lib.bp_gccb_simulate(None, A.ctypes.data, 2, s.ctypes.data, 1, -1.0, 0, 0, None, oi.ctypes.data),
+        "bp_gccb_simulate_batch": lambda: lib.bp_gccb_simulate_batch(None, A.ctypes.data, 2, s.ctypes.data, 1, 0, 0, None, 0, oi.ctypes.data),
+    }
+    declared = set(_header_symbols()) - {"bp_abi_version", "bp_create", "bp_create_on_stream", "bp_destroy", "bp_last_error", "bp_launch_count"}
+    assert declared == set(calls), declared ^ set(calls)
+    for name, call in calls.items():
+        assert call() == _native.BP_ERR_INVALID, name
+        assert b"NULL" in lib.bp_last_error(None), name
+    assert lib.bp_launch_count(None) == 0 and lib.bp_destroy(None) == _native.BP_OK
