@@ -77,6 +77,19 @@ def _generate_with_reference_fall_through(self):
 _ssf.SimulationStrategyFactory.generate_strategy = _generate_with_reference_fall_through
 
 
+def pytest_runtest_setup(item):
+    """The reference's tests are statistical and unseeded (each accepts with probability 1 - 1e-4 or so); seeding both
+    generators from the test's name makes this run reproducible: once green, always green."""
+    import random
+    import zlib
+
+    import numpy
+
+    key = zlib.crc32(item.nodeid.encode())
+    numpy.random.seed(key)
+    random.seed(key)
+
+
 def pytest_terminal_summary(terminalreporter):
     terminalreporter.write_line(f"factory requests for members outside the drop-in, served by reference classes: {FELL_THROUGH[0]}")
     terminalreporter.write_line(f"theboss -> theboss_b200 for {len(ALIASED)} modules: " + ", ".join(sorted(ALIASED)))
