@@ -97,8 +97,12 @@ static int bp_create_impl(int device, void *stream, bool own, bp_handle *out) {
     } else {
         h->stream = (cudaStream_t)stream;
     }
-    cudaEventCreate(&h->ev0);
-    cudaEventCreate(&h->ev1);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return bp_fail(nullptr, BP_ERR_CUDA, "bp_create: cudaEventCreate: %s", cudaGetErrorString(e));
+    }
     snprintf(h->err, sizeof(h->err), "no error");
     *out = h;
     return BP_OK;
