@@ -75,10 +75,16 @@ def main():
                     loops.append((by_addr[tgt], k))
     best = None
     for a, b in loops:
-        fp64 = sum(1 for x in ins[a:b + 1] if opcode(x["text"]) in ("DFMA", "DMUL", "DADD"))
+        fp64 = sum(1 for x in ins[a:b + 1] if opcode(x["text"]) in ("DFMA", "DMUL"))   # (DADD-heavy loops are the double-double reductions)
         inner = not any((a2 > a or b2 < b) and a2 >= a and b2 <= b and (a2, b2) != (a, b) for a2, b2 in loops)
         if best is None or fp64 > best[0]:
             best = (fp64, a, b, inner)
+    if "-loops" in sys.argv:
+        for a2, b2 in sorted(set(loops)):
+            seg = ins[a2:b2 + 1]
+            f = sum(1 for x in seg if opcode(x["text"]) in ("DFMA", "DMUL", "DADD"))
+            print(f"  loop {seg[0]['addr']:05x}..{seg[-1]['addr']:05x}: {len(seg)} instructions, FP64 {f}, LDS {sum(1 for x in seg if opcode(x['text']) == 'LDS')}, "
+                  f"local {sum(1 for x in seg if opcode(x['text']) in ('LDL', 'STL'))}, stall sum {sum(max(x['stall'], 1) for x in seg)}")
     fp64, a, b, _ = best
     body_ins = ins[a:b + 1]
     counts = {}

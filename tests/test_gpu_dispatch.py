@@ -47,7 +47,11 @@ def test_default_dispatch_matches_the_oracle(default_run):
     {"BP_K3_WARP_MAX_K": 8, "BP_K3_WIDE_MIN_K": 21},
     {"BP_K3_TPG": 2},                                 # up to hundreds of chunk blocks per sample
     {"BP_K3_TPG": 3, "BP_K3_WARP_MAX_K": 0, "BP_K3_CAP": 4},
-    {"BP_K3_MAX_C": 7},                               # more lanes per group, narrower columns
+    {"BP_K3_TREE_MAX_C": 8},                          # two lanes per term stream from k = 9
+    {"BP_K3_TREE_MAX_C": 6, "BP_K3_WARP_MAX_K": 0},   # two lanes from k = 7, four from k = 13
+    {"BP_K3_TREE_MAX_C": 6, "BP_K3_TPG": 5},
+    {"BP_K3_ENGINE": 0},                              # prefix x suffix scans instead of the product tree
+    {"BP_K3_ENGINE": 0, "BP_K3_MAX_C": 7},            # ... with more lanes per group, narrower columns
 ], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_every_block_shape_gives_the_same_samples(tmp_path, default_run, env):
     got = _run(tmp_path, "variant", **env)

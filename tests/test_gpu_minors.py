@@ -111,3 +111,44 @@ def test_shape_error(handle):
     U = workloads.haar(4, 1)
     with pytest.raises(AttributeError):
         handle.minors(U, np.array([1, 1, 0, 0], dtype=np.int32), np.array([1, 1, 0, 0], dtype=np.int32))
+
+
+LARGE_CASES = ["cf_k25", "bunched_k25", "cf_k26", "bunched_k26", "bunchedin_k26", "bunched_k28", "cf_k28", "bunchedin_k31", "dilated_k30"]
+
+
+@pytest.mark.parametrize("name", LARGE_CASES)
+def test_minors_beyond_one_lane_vs_long_double_fixtures(handle, golden_dir, name):
+    """k = 25 ... 31 (the steps of BASELINE config 5(ii): two and four lanes share the columns of a term) against the oracle's
+    80-bit sub-Ryser sweep (bs_cc_ryser_submatrices_permanent_calculator.py:80-119), computed once by
+    tests/golden/make_minors_large_golden.py: m = 2k Haar unitaries with collision-free / bunched outputs, bunched inputs, and
+    a k = 30 step in the 120-mode dilation of the config-5 lossy network."""
+    z = np.load(os.path.join(golden_dir, "minors_large.npz"))
+    if name not in list(z["names"]):
+        pytest.fail(f"fixture {name} missing from minors_large.npz")
+    k = int(name.split("_k")[1])
+    U = z[f"{name}_U"] if f"{name}_U" in z.files else workloads.haar(2 * k, 900 + k)
+    s, t, want = z[f"{name}_s"], z[f"{name}_t"], z[f"{name}_minors"]
+    assert int(s.sum()) == k and int(t.sum()) == k - 1
+    got = handle.minors(U, s, t)
+    assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max(), name
+    assert np.all(got[s == 0] == 0)
+    pmf = handle.gccb_pmf(U, s, t)
+    amp = (s * want) @ U.T                                       # sum_i s_i P_i U[j][i]
+    ref = np.abs(amp) ** 2
+    assert np.abs(pmf - ref / ref.sum()).max() <= 1e-10
+
+
+def test_k30_minors_in_the_dilated_network_satisfy_the_laplace_expansion(handle, golden_dir):
+    """Config 5(ii) at full size (k = 30 in the 120-mode dilation): sum_i s_i P_i U[j][i] = perm(U; s, t + e_j), right-hand side
+    from the batched single-permanent kernel (K2 walks the bunched output side of these items)."""
+    z = np.load(os.path.join(golden_dir, "minors_large.npz"))
+    U, s, t = z["dilated_k30_U"], z["dilated_k30_s"], z["dilated_k30_t"]
+    minors = handle.minors(U, s, t)
+    js = [0, 17, 59, 60, 101, 119]
+    S = np.repeat(s[None].astype(np.uint8), len(js), axis=0)
+    T = np.repeat(t[None].astype(np.uint8), len(js), axis=0)
+    T[np.arange(len(js)), js] += 1
+    singles = handle.perm_batched(U, S, T)
+    for q, j in enumerate(js):
+        lhs = np.sum(s * minors * U[j, :])
+        assert abs(lhs - singles[q]) <= REL_TOL * abs(singles[q]), j

@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbossperm.so")
+# BOSSPERM_LIB: another build of the same library (A/B measurements of compile-time tuning knobs); never a different backend
+LIB_PATH = os.environ.get("BOSSPERM_LIB") or os.path.join(_HERE, "lib", "libbossperm.so")
 
 BP_MAX_N = 40
 BP_MAX_MODES = 256

@@ -37,20 +37,73 @@ __device__ __forceinline__ cplx cshfl_xor(unsigned gmask, cplx a, int mask) {
 }
 
 // 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset
-template <int OFF>
+// (PIN: volatile, so that loads of the loop-invariant inner row stay inside the term loop instead of occupying registers)
+template <int OFF, bool PIN>
 __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
     double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    if (PIN) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    else     asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
     return v;
 }
 // c[j] += sg * X2row[j] for the C columns of a lane (row given by its shared-window address)
-template <int C, int J = 0>
+template <int C, bool PIN, int J = 0>
 __device__ __forceinline__ void k3_row_update(unsigned row, double sg, double (&cr)[C], double (&ci)[C]) {
     if constexpr (J < C) {
-        const double2 a = lds_f64x2<J * (int)sizeof(double2)>(row);
+        const double2 a = lds_f64x2<J * (int)sizeof(double2), PIN>(row);
         cr[J] = fma(sg, a.x, cr[J]);
         ci[J] = fma(sg, a.y, ci[J]);
-        k3_row_update<C, J + 1>(row, sg, cr, ci);
+        k3_row_update<C, PIN, J + 1>(row, sg, cr, ci);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Product engine 1: balanced product tree.  All C leave-one-out products of a term from an upward pass (node products,
+// C - 1 complex multiplies, depth ceil(log2 C)) and a downward pass (outside(child) = outside(parent) x sibling, the
+// leaf level fused into the accumulators): the same ~3C complex multiplies as prefix x suffix scans, but the dependency
+// depth is 2 log2 C instead of C and up to C / 2 multiplies are independent, so ONE warp keeps the FP64 pipe fed and a
+// lane can own all k <= 24 columns of a step (no shuffles, no butterfly multiplies).
+// node[MID] holds the product of the columns [LO, HI) with MID = (LO + HI) / 2 -- every internal node of the split tree
+// has its own MID in 1 .. C-1, so the indices are compile-time constants and the nodes live in registers.
+// ---------------------------------------------------------------------------------------------
+template <int C, int LO, int HI>
+__device__ __forceinline__ cplx k3_tree_val(const double (&cr)[C], const double (&ci)[C], const cplx (&node)[C]) {
+    if constexpr (HI - LO == 1) { cplx v = {cr[LO], ci[LO]}; return v; }
+    else return node[(LO + HI) / 2];
+}
+template <int C, int LO, int HI, bool ROOT>
+__device__ __forceinline__ void k3_tree_up(const double (&cr)[C], const double (&ci)[C], cplx (&node)[C]) {
+    if constexpr (HI - LO >= 2) {
+        constexpr int MID = (LO + HI) / 2;
+        k3_tree_up<C, LO, MID, true>(cr, ci, node);
+        k3_tree_up<C, MID, HI, true>(cr, ci, node);
+        if constexpr (ROOT) node[MID] = cmul(k3_tree_val<C, LO, MID>(cr, ci, node), k3_tree_val<C, MID, HI>(cr, ci, node));
+    }
+}
+template <int C, int LO, int HI>
+__device__ __forceinline__ void k3_tree_down(cplx out, const double (&cr)[C], const double (&ci)[C], const cplx (&node)[C],
+                                             double (&ar)[C], double (&ai)[C]) {
+    if constexpr (HI - LO == 1) { ar[LO] += out.re; ai[LO] += out.im; }
+    else {
+        constexpr int MID = (LO + HI) / 2;
+        const cplx L = k3_tree_val<C, LO, MID>(cr, ci, node), R = k3_tree_val<C, MID, HI>(cr, ci, node);
+        if constexpr (MID - LO == 1) cmul_acc(ar[LO], ai[LO], out, R);
+        else k3_tree_down<C, LO, MID>(cmul(out, R), cr, ci, node, ar, ai);
+        if constexpr (HI - MID == 1) cmul_acc(ar[MID], ai[MID], out, L);
+        else k3_tree_down<C, MID, HI>(cmul(out, L), cr, ci, node, ar, ai);
+    }
+}
+// root of the downward pass when the outside factor is the real term weight w (a lane that owns every column)
+template <int C>
+__device__ __forceinline__ void k3_tree_down_real(double w, const double (&cr)[C], const double (&ci)[C], const cplx (&node)[C],
+                                                  double (&ar)[C], double (&ai)[C]) {
+    if constexpr (C == 1) { ar[0] += w; }
+    else {
+        constexpr int MID = C / 2;
+        const cplx L = k3_tree_val<C, 0, MID>(cr, ci, node), R = k3_tree_val<C, MID, C>(cr, ci, node);
+        if constexpr (MID == 1) { ar[0] = fma(w, R.re, ar[0]); ai[0] = fma(w, R.im, ai[0]); }
+        else { cplx o = {w * R.re, w * R.im}; k3_tree_down<C, 0, MID>(o, cr, ci, node, ar, ai); }
+        if constexpr (C - MID == 1) { ar[MID] = fma(w, L.re, ar[MID]); ai[MID] = fma(w, L.im, ai[MID]); }
+        else { cplx o = {w * L.re, w * L.im}; k3_tree_down<C, MID, C>(o, cr, ci, node, ar, ai); }
     }
 }
 
@@ -74,6 +127,19 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C, int thre
 // three of its own four warps.
 #define K3_WARP_THREADS 32
 #define K3_WARP_PMAX 128
+// tree engine: register budgets (blocks of 128 threads per SM) and the widest lane that keeps the inner row in registers
+#ifndef K3_TREE_MINB4_MAX_C
+#define K3_TREE_MINB4_MAX_C 5
+#endif
+#ifndef K3_TREE_MINB3_MAX_C
+#define K3_TREE_MINB3_MAX_C 8
+#endif
+#ifndef K3_TREE_MINB3_MAX_C1
+#define K3_TREE_MINB3_MAX_C1 11
+#endif
+#ifndef K3_TREE_REGROW_MAX_C
+#define K3_TREE_REGROW_MAX_C 8
+#endif
 struct __align__(16) K3Step { double blow; int off; int pad; };
 __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, unsigned long long per_block) {
     unsigned long long a = (terms + per_block - 1) / per_block;
@@ -82,25 +148,30 @@ __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int ch
     return (int)a;
 }
 
-template <int LPG, int C, int THREADS>
+template <int LPG, int C, int THREADS, int ENG>
 struct K3Cfg {
     // same register budget per thread for both block sizes
-    static constexpr int MINB_128 = (C <= 5) ? 4 : (C <= 8) ? 3 : 2;
+    // (tree engine: the widest lanes that compile without spills under the 128- and 168-register caps)
+    static constexpr int MINB_128 = (ENG == 0) ? ((C <= 5) ? 4 : (C <= 8) ? 3 : 2)
+                                               : ((C <= K3_TREE_MINB4_MAX_C) ? 4 : (C <= (LPG == 1 ? K3_TREE_MINB3_MAX_C1 : K3_TREE_MINB3_MAX_C)) ? 3 : 2);
     static constexpr int MINB = (MINB_128 * GW_THREADS / THREADS) < 1 ? 1 : (MINB_128 * GW_THREADS / THREADS);
     static constexpr int PMAX = (THREADS >= GW_THREADS) ? K3_PMAX : K3_WARP_PMAX;
+    // row of the inner digit: in registers (4C of them) or re-read from shared memory at every sweep step
+    static constexpr bool REGROW = (ENG == 0) || (C <= K3_TREE_REGROW_MAX_C);
 };
 
 // grid = (chunks, launch slots).  order: NULL (slot = sample) or [slots] sample of every launch slot.
 // occ_s / occ_t: [samples][m] uint8 occupations (current input with the newly added particle; outputs
 // sampled so far).  partials: [slots][chunks][LPG*C][4] double-double partial sums.
-template <int LPG, int C, int THREADS>
-__global__ void __launch_bounds__(THREADS, K3Cfg<LPG, C, THREADS>::MINB)
+template <int LPG, int C, int THREADS, int ENG>
+__global__ void __launch_bounds__(THREADS, K3Cfg<LPG, C, THREADS, ENG>::MINB)
 k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const unsigned char *__restrict__ occ_s,
                  const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, const int *__restrict__ order,
                  int step, double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
     constexpr int W = LPG * C;
     constexpr int GROUPS = THREADS / LPG;
-    constexpr int PMAX = K3Cfg<LPG, C, THREADS>::PMAX;
+    constexpr int PMAX = K3Cfg<LPG, C, THREADS, ENG>::PMAX;
+    constexpr bool REGROW = K3Cfg<LPG, C, THREADS, ENG>::REGROW;
     extern __shared__ __align__(16) unsigned char k3_smem[];
     __shared__ GuanItem item;
     __shared__ short col_mode[W];
@@ -227,7 +298,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         unsigned off = 0;                                    // rows done in the current period
         int r0 = (row_start & 1ull) ? L0 : 0;               // reflected: odd rows sweep digit 0 downwards
         int dir0 = (row_start & 1ull) ? -1 : 1;
-        double cr[C], ci[C], x0r[C], x0i[C];
+        double cr[C], ci[C], x0r[REGROW ? C : 1], x0i[REGROW ? C : 1];
 #pragma unroll
         for (int j = 0; j < C; ++j) { cr[j] = 0.0; ci[j] = 0.0; }
         int par = r0;                                        // parity of sum(rho) -> sign of the term
@@ -255,8 +326,10 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         }
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            const double2 a = X2[col0 + j];                  // row of digit 0, kept in registers
-            x0r[j] = a.x; x0i[j] = a.y;
+            if constexpr (REGROW) {
+                const double2 a = X2[col0 + j];              // row of digit 0, kept in registers
+                x0r[j] = a.x; x0i[j] = a.y;
+            }
             if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
         }
         double sgn = (par & 1) ? -1.0 : 1.0;
@@ -300,68 +373,101 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 #pragma unroll 1
             for (int step = 0;; ++step) {
                 const double w = sgn * bout * w0;
-                // prefix products over this lane's columns, one chain per half
-                cplx pre[C];
-                pre[0].re = 1.0; pre[0].im = 0.0;
-                if (H > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
-#pragma unroll
-                for (int j = 2; j < H; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
-                cplx totA, totB = {1.0, 0.0};
-                if (H > 1) { cplx cl = {cr[H - 1], ci[H - 1]}; totA = cmul(pre[H - 1], cl); }
-                else       { totA.re = cr[0]; totA.im = ci[0]; }
-                if (H < C) {
-                    pre[H].re = 1.0; pre[H].im = 0.0;
-                    if (C - H > 1) { pre[H + 1].re = cr[H]; pre[H + 1].im = ci[H]; }
-#pragma unroll
-                    for (int j = H + 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
-                    if (C - H > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; totB = cmul(pre[C - 1], cl); }
-                    else           { totB.re = cr[C - 1]; totB.im = ci[C - 1]; }
-                }
-                // product of the other lanes' totals (xor butterfly inside the group)
-                cplx oth = {1.0, 0.0};
-                if (LPG > 1) {
-                    cplx all = (H < C) ? cmul(totA, totB) : totA;
-#pragma unroll
-                    for (int mask = 1; mask < LPG; mask <<= 1) {
-                        const cplx x = cshfl_xor(0xffffffffu, all, mask);
-                        oth = (mask == 1) ? x : cmul(oth, x);
-                        if ((mask << 1) < LPG) all = cmul(all, x);
+                bool last;
+                if constexpr (ENG == 0) {
+                    // prefix products over this lane's columns, one chain per half
+                    cplx pre[C];
+                    pre[0].re = 1.0; pre[0].im = 0.0;
+                    if (H > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
+    #pragma unroll
+                    for (int j = 2; j < H; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
+                    cplx totA, totB = {1.0, 0.0};
+                    if (H > 1) { cplx cl = {cr[H - 1], ci[H - 1]}; totA = cmul(pre[H - 1], cl); }
+                    else       { totA.re = cr[0]; totA.im = ci[0]; }
+                    if (H < C) {
+                        pre[H].re = 1.0; pre[H].im = 0.0;
+                        if (C - H > 1) { pre[H + 1].re = cr[H]; pre[H + 1].im = ci[H]; }
+    #pragma unroll
+                        for (int j = H + 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
+                        if (C - H > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; totB = cmul(pre[C - 1], cl); }
+                        else           { totB.re = cr[C - 1]; totB.im = ci[C - 1]; }
                     }
-                }
-                cplx seed = {w * oth.re, w * oth.im};
-                // next value of digit 0 (its weight is needed one term ahead)
-                const bool last = (step == L0);
-                if (!last) r0 += dir0;
-                w0 = bin0[r0];
-                // suffix passes: leave-one-out products, accumulated; the two halves seed each other's totals
-                if (H < C) {
-                    cplx sufB = cmul(seed, totA);
-#pragma unroll
-                    for (int j = C - 1; j >= H; --j) {
-                        if (j == H) { ar[H] += sufB.re; ai[H] += sufB.im; }
-                        else {
-                            cmul_acc(ar[j], ai[j], pre[j], sufB);
-                            cplx cj = {cr[j], ci[j]};
-                            sufB = cmul(sufB, cj);
+                    // product of the other lanes' totals (xor butterfly inside the group)
+                    cplx oth = {1.0, 0.0};
+                    if (LPG > 1) {
+                        cplx all = (H < C) ? cmul(totA, totB) : totA;
+    #pragma unroll
+                        for (int mask = 1; mask < LPG; mask <<= 1) {
+                            const cplx x = cshfl_xor(0xffffffffu, all, mask);
+                            oth = (mask == 1) ? x : cmul(oth, x);
+                            if ((mask << 1) < LPG) all = cmul(all, x);
                         }
                     }
-                }
-                cplx sufA = (H < C) ? cmul(seed, totB) : seed;
-#pragma unroll
-                for (int j = H - 1; j >= 0; --j) {
-                    if (j == 0) { ar[0] += sufA.re; ai[0] += sufA.im; }
-                    else {
-                        cmul_acc(ar[j], ai[j], pre[j], sufA);          // acc_j += prefix_j * suffix_j, fused
-                        cplx cj = {cr[j], ci[j]};
-                        sufA = cmul(sufA, cj);
+                    cplx seed = {w * oth.re, w * oth.im};
+                    // next value of digit 0 (its weight is needed one term ahead)
+                    last = (step == L0);
+                    if (!last) r0 += dir0;
+                    w0 = bin0[r0];
+                    // suffix passes: leave-one-out products, accumulated; the two halves seed each other's totals
+                    if (H < C) {
+                        cplx sufB = cmul(seed, totA);
+    #pragma unroll
+                        for (int j = C - 1; j >= H; --j) {
+                            if (j == H) { ar[H] += sufB.re; ai[H] += sufB.im; }
+                            else {
+                                cmul_acc(ar[j], ai[j], pre[j], sufB);
+                                cplx cj = {cr[j], ci[j]};
+                                sufB = cmul(sufB, cj);
+                            }
+                        }
                     }
+                    cplx sufA = (H < C) ? cmul(seed, totB) : seed;
+    #pragma unroll
+                    for (int j = H - 1; j >= 0; --j) {
+                        if (j == 0) { ar[0] += sufA.re; ai[0] += sufA.im; }
+                        else {
+                            cmul_acc(ar[j], ai[j], pre[j], sufA);          // acc_j += prefix_j * suffix_j, fused
+                            cplx cj = {cr[j], ci[j]};
+                            sufA = cmul(sufA, cj);
+                        }
+                    }
+                } else {
+                    // balanced product tree (see k3_tree_up / k3_tree_down)
+                    cplx node[C];
+                    bool last_t;
+                    if constexpr (LPG == 1) {
+                        k3_tree_up<C, 0, C, false>(cr, ci, node);
+                        last_t = (step == L0);
+                        if (!last_t) r0 += dir0;
+                        w0 = bin0[r0];
+                        k3_tree_down_real<C>(w, cr, ci, node, ar, ai);
+                    } else {
+                        k3_tree_up<C, 0, C, true>(cr, ci, node);
+                        cplx all = k3_tree_val<C, 0, C>(cr, ci, node), oth = {1.0, 0.0};
+#pragma unroll
+                        for (int mask = 1; mask < LPG; mask <<= 1) {
+                            const cplx x = cshfl_xor(0xffffffffu, all, mask);
+                            oth = (mask == 1) ? x : cmul(oth, x);
+                            if ((mask << 1) < LPG) all = cmul(all, x);
+                        }
+                        last_t = (step == L0);
+                        if (!last_t) r0 += dir0;
+                        w0 = bin0[r0];
+                        cplx seed = {w * oth.re, w * oth.im};
+                        k3_tree_down<C, 0, C>(seed, cr, ci, node, ar, ai);
+                    }
+                    last = last_t;
                 }
                 if (last) break;
                 // c -= 2 * dir0 * X[0]
                 sgn = -sgn;
                 const double sg = (dir0 > 0) ? -1.0 : 1.0;
+                if constexpr (REGROW) {
 #pragma unroll
-                for (int j = 0; j < C; ++j) { cr[j] = fma(sg, x0r[j], cr[j]); ci[j] = fma(sg, x0i[j], ci[j]); }
+                    for (int j = 0; j < C; ++j) { cr[j] = fma(sg, x0r[j], cr[j]); ci[j] = fma(sg, x0i[j], ci[j]); }
+                } else {
+                    k3_row_update<C, true>(x2c0, sg, cr, ci);
+                }
             }
             dir0 = -dir0;
             // ---- next row
@@ -369,7 +475,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             ++q;
             sgn = -sgn;
             bout = st.binom * blow_next;
-            k3_row_update<C>(row_next, sg_next, cr, ci);
+            k3_row_update<C, false>(row_next, sg_next, cr, ci);
         }
     }
 
@@ -606,21 +712,20 @@ struct K3Variant { k3_fn fn; int lpg, c, threads; };
 #define K3_MAX_C 12
 #define K3_WARP_MAX_C 8
 #define K3_WARP_DEFAULT_MAX_K 16
-static K3Variant g_k3[4][K3_MAX_C + 1];        // [log2 LPG][C], 128-thread blocks
-static K3Variant g_k3w[2][K3_WARP_MAX_C + 1];  // [log2 LPG][C], one-warp blocks (LPG <= 2: k <= 16)
+static K3Variant g_k3[4][K3_MAX_C + 1];        // engine 0 (prefix x suffix scans): [log2 LPG][C], 128-thread blocks
+static K3Variant g_k3w[2][K3_WARP_MAX_C + 1];  // engine 0, one-warp blocks (LPG <= 2: k <= 16)
+// engine 1 (product tree): one lane owns all columns up to k = K3_TREE_MAX_C1, two (four) lanes share them beyond
+#define K3_TREE_MAX_C1 19   // widest lanes that compile without spills: 19 / 15 / 12 columns for 1 / 2 / 4 lanes per group
+#define K3_TREE_MAX_C2 15
+#define K3_TREE_WARP_MAX_C 16
+#define K3_TREE_MAX_C4 12
+static K3Variant g_k3t[3][K3_TREE_MAX_C1 + 1];     // [log2 LPG][C], 128-thread blocks
+static K3Variant g_k3tw[K3_TREE_WARP_MAX_C + 1];   // LPG = 1, one-warp blocks
 
 template <int LPG, int C>
 static void k3_reg(int lg) {
-    g_k3[lg][C].fn = k3_minors_kernel<LPG, C, GW_THREADS>;
-    g_k3[lg][C].lpg = LPG;
-    g_k3[lg][C].c = C;
-    g_k3[lg][C].threads = GW_THREADS;
-    if constexpr (LPG <= 2 && C <= K3_WARP_MAX_C) {
-        g_k3w[lg][C].fn = k3_minors_kernel<LPG, C, K3_WARP_THREADS>;
-        g_k3w[lg][C].lpg = LPG;
-        g_k3w[lg][C].c = C;
-        g_k3w[lg][C].threads = K3_WARP_THREADS;
-    }
+    g_k3[lg][C] = K3Variant{k3_minors_kernel<LPG, C, GW_THREADS, 0>, LPG, C, GW_THREADS};
+    if constexpr (LPG <= 2 && C <= K3_WARP_MAX_C) g_k3w[lg][C] = K3Variant{k3_minors_kernel<LPG, C, K3_WARP_THREADS, 0>, LPG, C, K3_WARP_THREADS};
 }
 template <int LPG>
 static void k3_reg_all(int lg) {
@@ -628,27 +733,60 @@ static void k3_reg_all(int lg) {
     k3_reg<LPG, 5>(lg); k3_reg<LPG, 6>(lg); k3_reg<LPG, 7>(lg); k3_reg<LPG, 8>(lg);
     k3_reg<LPG, 9>(lg); k3_reg<LPG, 10>(lg); k3_reg<LPG, 11>(lg); k3_reg<LPG, 12>(lg);
 }
+template <int C>
+static void k3_reg_tree() {
+    g_k3t[0][C] = K3Variant{k3_minors_kernel<1, C, GW_THREADS, 1>, 1, C, GW_THREADS};
+    if constexpr (C <= K3_TREE_WARP_MAX_C) g_k3tw[C] = K3Variant{k3_minors_kernel<1, C, K3_WARP_THREADS, 1>, 1, C, K3_WARP_THREADS};
+    if constexpr (C <= K3_TREE_MAX_C2 && C >= 5) g_k3t[1][C] = K3Variant{k3_minors_kernel<2, C, GW_THREADS, 1>, 2, C, GW_THREADS};
+    if constexpr (C <= K3_TREE_MAX_C4 && C >= 5) g_k3t[2][C] = K3Variant{k3_minors_kernel<4, C, GW_THREADS, 1>, 4, C, GW_THREADS};
+    if constexpr (C > 1) k3_reg_tree<C - 1>();
+}
 
-// Variant for k input columns: smallest padded width LPG * C >= k with C <= max_c, preferring fewer lanes per
-// group.  max_c is 8, except k = 17 .. 24 where two lanes with up to 12 columns beat four lanes with up to 6 (no
-// butterfly multiplies; 2 warps/SMSP): 4 % at k = 21 .. 24, 7 % on a whole n = 20 run for k = 17 .. 20
-// (profiles/r01_k3_block_shapes.txt).  Steps k <= K3_WARP_DEFAULT_MAX_K run in one-warp blocks.
-// Tuning knobs, read once: BP_K3_MAX_C (column limit for all k), BP_K3_WIDE_MIN_K (first k of the two-lane rule),
-// BP_K3_WARP_MAX_K (0 = never one-warp blocks).
+// Variant for k input columns.
+//   engine 1 (default): product tree; one lane per term stream with all k <= 19 columns, two lanes with ceil(k / 2) columns
+//     each for k = 20 .. 30, four lanes for k = 31 .. 48; one-warp blocks for the steps k <= K3_WARP_DEFAULT_MAX_K whose
+//     walk fits one block.
+//   engine 0 (BP_K3_ENGINE=0, kept for A/B measurements): smallest padded width LPG * C >= k with C <= max_c, preferring
+//     fewer lanes per group; max_c is 8, except k = 17 .. 24 where two lanes with up to 12 columns beat four with up to 6.
+// Tuning knobs, read once: BP_K3_ENGINE, BP_K3_MAX_C (engine 0: column limit for all k), BP_K3_WIDE_MIN_K (engine 0: first k
+// of the two-lane rule), BP_K3_WARP_MAX_K (0 = never one-warp blocks), BP_K3_TREE_MAX_C (engine 1: column limit per lane).
 #define K3_DEFAULT_MAX_C 8
 static K3Variant k3_pick(int k) {
-    static int forced_max_c = 0, warp_max_k = K3_WARP_DEFAULT_MAX_K, wide_min_k = 17;
+    static int forced_max_c = 0, warp_max_k = K3_WARP_DEFAULT_MAX_K, wide_min_k = 17, engine = 1, tree_max_c1 = K3_TREE_MAX_C1;
     static const bool ready = [] {   // thread-safe one-time registration (C++11 static initialisation)
+#ifdef K3_DEV_C   // development builds: a single instantiation (seconds to compile; for SASS inspection only)
+        g_k3t[0][K3_DEV_C] = K3Variant{k3_minors_kernel<K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS, K3_DEV_ENG>, K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS};
+#else
         k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3);
+        k3_reg_tree<K3_TREE_MAX_C1>();
+#endif
         const char *e = getenv("BP_K3_MAX_C");
         forced_max_c = e ? atoi(e) : 0;
         if (forced_max_c > K3_MAX_C) forced_max_c = K3_MAX_C;
         if ((e = getenv("BP_K3_WARP_MAX_K"))) warp_max_k = atoi(e);
-        if (warp_max_k > 2 * K3_WARP_MAX_C) warp_max_k = 2 * K3_WARP_MAX_C;
         if ((e = getenv("BP_K3_WIDE_MIN_K"))) wide_min_k = atoi(e);
+        if ((e = getenv("BP_K3_ENGINE"))) engine = atoi(e) ? 1 : 0;
+        if ((e = getenv("BP_K3_TREE_MAX_C"))) tree_max_c1 = atoi(e);
+        if (tree_max_c1 > K3_TREE_MAX_C1) tree_max_c1 = K3_TREE_MAX_C1;
+        if (tree_max_c1 < 6) tree_max_c1 = 6;
         return true;
     }();
     (void)ready;
+    K3Variant none = {nullptr, 0, 0, 0};
+    if (k < 1) return none;
+    if (engine == 1) {
+        // fewest lanes per group whose column count fits the lane limit
+        for (int lg = 0; lg < 3; ++lg) {
+            const int lpg = 1 << lg, c = (k + lpg - 1) / lpg;
+            const int lim = lg == 0 ? tree_max_c1 : lg == 1 ? (tree_max_c1 < K3_TREE_MAX_C2 ? tree_max_c1 : K3_TREE_MAX_C2)
+                                                            : (tree_max_c1 < K3_TREE_MAX_C4 ? tree_max_c1 : K3_TREE_MAX_C4);
+            if (c > lim) continue;
+            if (lg == 0 && k <= warp_max_k && k <= K3_TREE_WARP_MAX_C) return g_k3tw[k];
+            if (g_k3t[lg][c].fn) return g_k3t[lg][c];
+        }
+        // beyond the tree variants: fall through to the scan engine's eight-lane layouts
+    }
+    const int wmax = warp_max_k > 2 * K3_WARP_MAX_C ? 2 * K3_WARP_MAX_C : warp_max_k;
     int max_c = (k >= wide_min_k && k <= 24) ? K3_MAX_C : K3_DEFAULT_MAX_C;
     if (forced_max_c >= 7) max_c = forced_max_c;
     int best_lg = -1, best_c = 0, best_w = 1 << 30;
@@ -658,9 +796,8 @@ static K3Variant k3_pick(int k) {
         if (c > max_c) continue;
         if (lpg * c < best_w) { best_w = lpg * c; best_lg = lg; best_c = c; }
     }
-    K3Variant none = {nullptr, 0, 0, 0};
     if (best_lg < 0) return none;
-    if (k <= warp_max_k && best_lg <= 1 && best_c <= K3_WARP_MAX_C) return g_k3w[best_lg][best_c];
+    if (k <= wmax && best_lg <= 1 && best_c <= K3_WARP_MAX_C) return g_k3w[best_lg][best_c];
     return g_k3[best_lg][best_c];
 }
 
