@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Register-file read model of an FP64 loop (no GPU needed).  Measured on B200 (scripts/rf_probe.cu, profiles/r02_rf_probe.txt): an
+SMSP reads ONE 64-bit vector-register operand per cycle, so an FP64 instruction costs max(2 cycles of the pipe [2.18 for DFMA],
+number of source operands NOT served by the operand reuse cache).  Prints, for the innermost loop with the most FP64
+instructions (or the loop starting at a given address), the FP64 instruction count, the pipe-only bound and the
+register-read bound in cycles per iteration per warp.
+
+usage: sass_rf.py <object-or-so> <kernel-name-substring> [loop-start-address-hex]"""
+import re, subprocess, sys
+
+def main():
+    path, kernel = sys.argv[1], sys.argv[2]
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    body = None
+    for b in re.split(r"\n\s*Function : ", out)[1:]:
+        if kernel in b.split("\n", 1)[0]:
+            body = b; break
+    if body is None: raise SystemExit("kernel not found")
+    ins = []
+    for m in re.finditer(r"/\*([0-9a-f]{4,})\*/\s+(.*?);", body):
+        ins.append((int(m.group(1), 16), m.group(2).strip()))
+    by_addr = {a: i for i, (a, _) in enumerate(ins)}
+    loops = []
+    for i, (a, t) in enumerate(ins):
+        if re.match(r"(@!?U?P\d+\s+)?BRA\b", t):
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) in by_addr and by_addr[int(m.group(1), 16)] <= i:
+                loops.append((by_addr[int(m.group(1), 16)], i))
+    def fp(t):
+        t = re.sub(r"^@!?U?P\d+\s+", "", t)
+        return t.split()[0].split(".")[0] in ("DFMA", "DMUL", "DADD")
+    if len(sys.argv) > 3:
+        start = int(sys.argv[3], 16)
+        cand = [l for l in loops if ins[l[0]][0] == start]
+    else:
+        inner = [l for l in loops if not any(l2 != l and l2[0] >= l[0] and l2[1] <= l[1] for l2 in loops)]
+        cand = sorted(inner, key=lambda l: -sum(fp(t) for _, t in ins[l[0]:l[1] + 1]))
+    a, b = cand[0]
+    seg = ins[a:b + 1]
+    cache = [None, None, None]
+    n = {"DFMA": 0, "DMUL": 0, "DADD": 0}
+    pipe = rf = both = 0.0
+    hist = {}
+    for _, t in seg + seg:            # two passes: the second one sees the reuse state left by the loop tail
+        pass
+    for rep in range(2):
+        if rep == 1: n = {"DFMA": 0, "DMUL": 0, "DADD": 0}; pipe = rf = both = 0.0; hist = {}
+        for _, t in seg:
+            t0 = re.sub(r"^@!?U?P\d+\s+", "", t)
+            op = t0.split()[0].split(".")[0]
+            if op not in n:
+                continue                      # (other instructions also read registers; they are few and mostly 32-bit)
+            ops = [x.strip() for x in t0.split(None, 1)[1].split(",")][1:]
+            reads = 0
+            newc = [None, None, None]
+            for s, o in enumerate(ops[:3]):
+                r = re.match(r"[-|]*\s*(R\d+)(\.reuse)?", o.replace("|", ""))
+                if not r: continue           # immediate / constant / uniform operand
+                if r.group(1) == "RZ": continue
+                if cache[s] != r.group(1): reads += 1
+                if r.group(2): newc[s] = r.group(1)
+            cache = newc
+            n[op] += 1
+            p = 2.18 if op == "DFMA" else 2.0
+            pipe += p; rf += reads; both += max(p, reads)
+            hist[(op, reads)] = hist.get((op, reads), 0) + 1
+    tot = sum(n.values())
+    print(f"loop {seg[0][0]:05x}..{seg[-1][0]:05x}: {len(seg)} instructions, FP64 {tot} {n}")
+    print(f"  pipe-only bound {pipe:.0f} cycles/iteration, register reads {rf:.0f}, max(pipe, reads) per instruction: {both:.0f} cycles"
+          f"  -> ceiling of sm__pipe_fp64_cycles_active = {100.0 * 2 * tot / both:.1f} %")
+    print("  (instruction, 64-bit register reads): count ", dict(sorted(hist.items())))
+
+if __name__ == "__main__":
+    main()

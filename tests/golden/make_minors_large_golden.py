@@ -38,7 +38,12 @@ def case_inputs(name):
         _, U_lossy, _ = workloads.c5_lossy(30, 60)
         U = np.ascontiguousarray(prepare_interferometer_matrix_in_expanded_space(U_lossy))
         s = np.array([1] * k + [0] * (120 - k), dtype=np.int32)
-        t = _occ(rng, 120, k - 1)
+        # a POSSIBLE outcome: a loss mode (rows 60 ..) couples to exactly one input mode, so only the loss modes of
+        # occupied inputs may hold a particle (any other placement has permanent 0): 11 lost particles + 18 detected ones
+        t = np.zeros(120, dtype=np.int32)
+        for i in rng.choice(k, 11, replace=False):
+            t[60 + int(np.argmax(np.abs(U[60:, i])))] += 1
+        t[:60:6] += _occ(rng, 10, k - 1 - 11)          # bunched detections (every sixth mode): a ~2^24-term walk for the oracle
         return U, s, t
     m = 2 * k
     U = workloads.haar(m, 900 + k)
@@ -59,11 +64,26 @@ def case_inputs(name):
 CASES = ["cf_k25", "bunched_k25", "cf_k26", "bunched_k26", "bunchedin_k26", "bunchedin_k31", "bunched_k28", "cf_k28", "dilated_k30"]
 
 
+# Ryser-form sums lose about one bit per particle: the 80-bit sub-Ryser sweep is good to ~2^k * 5e-20 (1.5e-11 at k = 28,
+# 1.2e-10 at k = 31).  The cases beyond k = 28 therefore take every minor from its definition -- the single permanent with one
+# input particle removed -- in the Chin-Huh form (chin_huh_permanent_calculator.py:38-59, no cancellation growth), walked
+# over the bunched OUTPUT occupation through perm(U; s, t) = perm(U^T; t, s).
+CH_SINGLES = {"bunchedin_k31", "dilated_k30"}
+
+
 def run(name):
     from oracle import pyoracle as orc
     U, s, t = case_inputs(name)
     t0 = time.time()
-    minors = orc.submatrices(U, s, t, orc.RYSER, "ld")
+    if name in CH_SINGLES:
+        UT = np.ascontiguousarray(U.T)
+        minors = np.zeros(len(s), dtype=np.complex128)
+        for i in np.nonzero(s)[0]:
+            si = s.copy()
+            si[i] -= 1
+            minors[i] = orc.guan_permanent(UT, t, si, orc.CHIN_HUH, "ld")
+    else:
+        minors = orc.submatrices(U, s, t, orc.RYSER, "ld")
     return name, U, s, t, minors, time.time() - t0
 
 

@@ -1,7 +1,7 @@
 """K3 dispatch (GPU): every block shape / work split the launcher can choose must give the same answers.
 
-The knobs (BP_K3_WARP_MAX_K: one-warp blocks for small steps, BP_K3_WIDE_MIN_K: two-lane variants, BP_K3_TPG /
-BP_K3_CAP: terms per lane group and chunk blocks per sample) are read once per process, so every setting runs the
+The knobs (BP_K3_WARP_MAX_K: one-warp blocks for small steps, BP_K3_TREE_MAX_C: columns per lane, i.e. from which k two and
+four lanes share a term stream, BP_K3_TPG / BP_K3_CAP: terms per lane group and chunk blocks per sample) are read once per process, so every setting runs the
 same jobs in a fresh interpreter (tests/_knob_job.py).  The default setting is checked against the oracle's sampling
 loop on the same decision tape; the others against the default.  Tiny BP_K3_TPG values force many chunk blocks per
 sample at small k, which exercises the multi-sample 512-thread chunk reduction of the finish kernel and the
@@ -44,14 +44,13 @@ def test_default_dispatch_matches_the_oracle(default_run):
 
 @pytest.mark.parametrize("env", [
     {"BP_K3_WARP_MAX_K": 0},                          # 128-thread blocks everywhere
-    {"BP_K3_WARP_MAX_K": 8, "BP_K3_WIDE_MIN_K": 21},
+    {"BP_K3_WARP_MAX_K": 8},
     {"BP_K3_TPG": 2},                                 # up to hundreds of chunk blocks per sample
     {"BP_K3_TPG": 3, "BP_K3_WARP_MAX_K": 0, "BP_K3_CAP": 4},
     {"BP_K3_TREE_MAX_C": 8},                          # two lanes per term stream from k = 9
     {"BP_K3_TREE_MAX_C": 6, "BP_K3_WARP_MAX_K": 0},   # two lanes from k = 7, four from k = 13
     {"BP_K3_TREE_MAX_C": 6, "BP_K3_TPG": 5},
-    {"BP_K3_ENGINE": 0},                              # prefix x suffix scans instead of the product tree
-    {"BP_K3_ENGINE": 0, "BP_K3_MAX_C": 7},            # ... with more lanes per group, narrower columns
+    {"BP_K3_TREE_MAX_C": 7, "BP_K3_TPG": 1},          # every lane group gets a single short period: Guan step at every boundary
 ], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_every_block_shape_gives_the_same_samples(tmp_path, default_run, env):
     got = _run(tmp_path, "variant", **env)

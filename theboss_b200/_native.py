@@ -100,6 +100,17 @@ def as_state(state, m: Optional[int] = None) -> np.ndarray:
     return out
 
 
+def occupations_u8(x) -> np.ndarray:
+    """Occupation table -> C-contiguous uint8; counts outside 0 .. 255 raise instead of wrapping (the int32 entry points
+    check the same on the C side)."""
+    a = np.asarray(x)
+    if a.dtype != np.uint8:
+        if a.size and (a.min() < 0 or a.max() > 255):
+            raise ValueError("occupation numbers must lie in 0 .. 255")
+        a = a.astype(np.uint8)
+    return np.ascontiguousarray(a)
+
+
 class Handle:
     """One device + one stream + scratch (bp_handle).  Created lazily, never pickled."""
 
@@ -113,14 +124,23 @@ class Handle:
         if rc != BP_OK:
             raise BossPermError(rc, self._lib.bp_last_error(None).decode())
         self.device = int(device)
+        # The handle is NOT thread-safe on the C side (one pinned staging buffer, one set of scratch slots, one K1 arrival
+        # counter).  ctypes releases the GIL during a call, so two Python threads that share the process-wide default handle --
+        # independent calculator objects, safe in the reference -- would otherwise run bp_* concurrently on it: every call goes
+        # through _call, which serialises the callers of one handle.
+        self._lock = threading.RLock()
 
     # -- plumbing ----------------------------------------------------------------------------
-    def _check(self, rc: int):
-        if rc != BP_OK:
+    def _call(self, name: str, *args):
+        """One C-ABI call on this handle under the handle's lock; the error text is read before the lock is released."""
+        with self._lock:
+            rc = getattr(self._lib, name)(self._h, *args)
+            if rc == BP_OK:
+                return
             msg = self._lib.bp_last_error(self._h).decode()
-            if rc == BP_ERR_SHAPE:
-                raise AttributeError(msg)   # bs_permanent_calculator_base.py:179-180
-            raise BossPermError(rc, msg)
+        if rc == BP_ERR_SHAPE:
+            raise AttributeError(msg)   # bs_permanent_calculator_base.py:179-180
+        raise BossPermError(rc, msg)
 
     @staticmethod
     def _normalised(U, s, t):
@@ -153,27 +173,27 @@ class Handle:
             pass
 
     def synchronize(self):
-        self._check(self._lib.bp_synchronize(self._h))
+        self._call("bp_synchronize")
 
     def device_info(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        self._check(self._lib.bp_device_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self._call("bp_device_info", C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return {"sm_count": a.value, "cc": (b.value, c.value), "clock_khz": d.value}
 
     def launch_count(self) -> int:
         return int(self._lib.bp_launch_count(self._h))
 
     def timer_start(self):
-        self._check(self._lib.bp_timer_start(self._h))
+        self._call("bp_timer_start")
 
     def timer_stop(self) -> float:
         ms = C.c_float()
-        self._check(self._lib.bp_timer_stop(self._h, C.byref(ms)))
+        self._call("bp_timer_stop", C.byref(ms))
         return float(ms.value)
 
     def fp64_peak(self, target_ms: float = 200.0) -> float:
         tf = C.c_double()
-        self._check(self._lib.bp_fp64_peak(self._h, float(target_ms), C.byref(tf)))
+        self._call("bp_fp64_peak", float(target_ms), C.byref(tf))
         return float(tf.value)
 
     # -- K1 ----------------------------------------------------------------------------------
@@ -182,47 +202,50 @@ class Handle:
         if A.shape[0] != A.shape[1]:
             raise AttributeError
         out = (C.c_double * 2)()
-        self._check(self._lib.bp_glynn_matrix(self._h, A.ctypes.data, A.shape[0], out))
+        self._call("bp_glynn_matrix", A.ctypes.data, A.shape[0], out)
         return complex(out[0], out[1])
 
     def glynn_matrix_range(self, A: np.ndarray, lo: int, hi: int):
         """Un-normalised double-double partial (re_hi, re_lo, im_hi, im_lo) over Gray steps [lo, hi)."""
         A = as_matrix(A)
+        if A.shape[0] != A.shape[1]:
+            raise AttributeError("glynn_matrix_range needs a square matrix")
+        if not 0 <= int(lo) <= int(hi):
+            raise ValueError(f"Gray-step range [{lo}, {hi}) is not ordered")
         out = (C.c_double * 4)()
-        self._check(self._lib.bp_glynn_matrix_range(self._h, A.ctypes.data, A.shape[0], int(lo), int(hi), out))
+        self._call("bp_glynn_matrix_range", A.ctypes.data, A.shape[0], int(lo), int(hi), out)
         return tuple(out)
 
     def glynn_matrix_range_dev(self, dA_ptr: int, N: int, lo: int, hi: int, d_out_ptr: int):
-        self._check(self._lib.bp_glynn_matrix_range_dev(self._h, C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_ptr)))
+        self._call("bp_glynn_matrix_range_dev", C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_ptr))
 
     def glynn_single(self, U: np.ndarray, s: np.ndarray, t: np.ndarray) -> complex:
         U, s, t = self._normalised(U, s, t)
         out = (C.c_double * 2)()
-        self._check(self._lib.bp_glynn_single(self._h, U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, out))
+        self._call("bp_glynn_single", U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, out)
         return complex(out[0], out[1])
 
     # -- K2 ----------------------------------------------------------------------------------
     def perm_batched(self, U: np.ndarray, S: np.ndarray, T: np.ndarray, formula: int = FORMULA_GLYNN) -> np.ndarray:
         U = as_matrix(U)
-        S = np.ascontiguousarray(S, dtype=np.uint8)
-        T = np.ascontiguousarray(T, dtype=np.uint8)
+        S, T = occupations_u8(S), occupations_u8(T)
         if S.shape != T.shape or S.ndim != 2 or S.shape[1] != U.shape[0]:
             raise AttributeError
         out = np.zeros(S.shape[0], dtype=np.complex128)
-        self._check(self._lib.bp_perm_batched(self._h, U.ctypes.data, U.shape[0], S.ctypes.data, T.ctypes.data,
-                                              S.shape[0], int(formula), out.ctypes.data))
+        self._call("bp_perm_batched", U.ctypes.data, U.shape[0], S.ctypes.data, T.ctypes.data,
+                                              S.shape[0], int(formula), out.ctypes.data)
         return out
 
     def perm_batched_dev(self, dU: int, m: int, dS: int, dT: int, B: int, formula: int, d_out: int):
-        self._check(self._lib.bp_perm_batched_dev(self._h, C.c_void_p(dU), int(m), C.c_void_p(dS), C.c_void_p(dT),
-                                                  int(B), int(formula), C.c_void_p(d_out)))
+        self._call("bp_perm_batched_dev", C.c_void_p(dU), int(m), C.c_void_p(dS), C.c_void_p(dT),
+                                                  int(B), int(formula), C.c_void_p(d_out))
 
     # -- K3 ----------------------------------------------------------------------------------
     def minors(self, U: np.ndarray, s: np.ndarray, t: np.ndarray, formula: int = FORMULA_CHIN_HUH) -> np.ndarray:
         U, s, t = self._normalised(U, s, t)
         out = np.zeros(U.shape[0], dtype=np.complex128)
-        self._check(self._lib.bp_minors(self._h, U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, int(formula),
-                                        out.ctypes.data))
+        self._call("bp_minors", U.ctypes.data, U.shape[0], s.ctypes.data, t.ctypes.data, int(formula),
+                                        out.ctypes.data)
         return out
 
     def gccb_pmf(self, U: np.ndarray, s: np.ndarray, t: np.ndarray, want_minors: bool = False):
@@ -230,8 +253,8 @@ class Handle:
         m = U.shape[0]
         pmf = np.zeros(m, dtype=np.float64)
         minors = np.zeros(m, dtype=np.complex128) if want_minors else None
-        self._check(self._lib.bp_gccb_pmf(self._h, U.ctypes.data, m, s.ctypes.data, t.ctypes.data, pmf.ctypes.data,
-                                          minors.ctypes.data if want_minors else None))
+        self._call("bp_gccb_pmf", U.ctypes.data, m, s.ctypes.data, t.ctypes.data, pmf.ctypes.data,
+                                          minors.ctypes.data if want_minors else None)
         return (pmf, minors) if want_minors else pmf
 
     # -- K3 + K4 -----------------------------------------------------------------------------
@@ -247,8 +270,8 @@ class Handle:
             if tape.shape != (int(n_samples), 1 + 2 * n):
                 raise ValueError(f"decision tape must have shape ({n_samples}, {1 + 2 * n})")
             tp = tape.ctypes.data
-        self._check(self._lib.bp_gccb_simulate(self._h, U.ctypes.data, m, s.ctypes.data, int(n_samples), float(eta),
-                                               int(seed) & (2 ** 64 - 1), int(first_sample), tp, out.ctypes.data))
+        self._call("bp_gccb_simulate", U.ctypes.data, m, s.ctypes.data, int(n_samples), float(eta),
+                                               int(seed) & (2 ** 64 - 1), int(first_sample), tp, out.ctypes.data)
         return out
 
     def gccb_simulate_batch(self, Us: np.ndarray, states: np.ndarray, seed: int = 0, first_sample: int = 0,
@@ -267,8 +290,8 @@ class Handle:
             if tape.shape[0] != S or tape.shape[1] != 1 + 2 * tn or tn < int(states.sum(axis=1).max(initial=0)):
                 raise ValueError("decision tape must have shape (S, 1 + 2 * n_max)")
             tp = tape.ctypes.data
-        self._check(self._lib.bp_gccb_simulate_batch(self._h, Us.ctypes.data, m, states.ctypes.data, S, int(seed) & (2 ** 64 - 1),
-                                                     int(first_sample), tp, tn, out.ctypes.data))
+        self._call("bp_gccb_simulate_batch", Us.ctypes.data, m, states.ctypes.data, S, int(seed) & (2 ** 64 - 1),
+                                                     int(first_sample), tp, tn, out.ctypes.data)
         return out
 
 

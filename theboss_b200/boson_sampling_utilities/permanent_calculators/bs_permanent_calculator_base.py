@@ -81,7 +81,7 @@ class BSPermanentCalculatorBase(BSPermanentCalculatorInterface):
         U, s, t = self._device_operands()
         if int(s.sum()) != int(t.sum()):
             raise AttributeError("input and output states hold different particle numbers")
-        out = self._handle().perm_batched(U, s[None, :].astype(np.uint8), t[None, :].astype(np.uint8), self._formula)
+        out = self._handle().perm_batched(U, s[None, :], t[None, :], self._formula)
         return np.complex128(out[0])
 
 

@@ -14,14 +14,21 @@
 // the k INPUT particles (columns of U repeated by s):
 //     c_col(rho) = sum_j (t_j - 2 rho_j) U[j][mode(col)]
 //     P_col      = 2^-(k-1) sum_rho (-1)^{sum rho} prod_j C(t_j, rho_j) prod_{col' != col} c_col'
-// All k leave-one-out products of a term come from prefix x suffix products: ~3k complex
-// multiplies per term instead of k^2.
+// All k leave-one-out products of a term come from a balanced product tree: ~3k complex multiplies per
+// term instead of k^2.
 //
-// Thread mapping: LPG (1, 2, 4 or 8) adjacent lanes form a group that walks one contiguous range
-// of terms; each lane owns C columns (LPG * C >= k, padding columns are the constant 1).  A lane
-// keeps c[C], prefix[C] and its C accumulators in registers; the product of the OTHER lanes'
-// column products reaches it through an xor-butterfly of warp shuffles and seeds its suffix pass,
-// so splitting costs only (log2 LPG) complex multiplies per term.
+// Thread mapping: LPG (1, 2 or 4) adjacent lanes form a group that walks one contiguous range of terms; each
+// lane owns C columns (LPG * C >= k, padding columns are the constant 1).  A lane keeps c[C], the tree nodes
+// and its C accumulators in registers; the product of the OTHER lanes' column products reaches it through an
+// xor-butterfly of warp shuffles and seeds its downward pass, so splitting costs only (log2 LPG) complex
+// multiplies per term.
+//
+// What bounds the term loop (measured, scripts/rf_probe.cu -> profiles/r02_rf_probe.txt): an SMSP reads ONE 64-bit
+// vector-register operand per cycle, so a DFMA whose three sources are distinct registers costs 3 cycles where the FP64
+// pipe needs 2; only operands repeated from the previous instruction (operand reuse cache) are free.  The loop below is a
+// DFMA / DMUL / DADD mix of 90 / 45 / 25 instructions per term at C = 12, of which ptxas pairs 37 DFMAs: 380 cycles per
+// term against 320 of pure pipe time (scripts/sass_rf.py) -- exactly the measured rate.  More warps per SMSP do not help
+// (profiles/r02_k3_history.txt); fewer distinct operands per instruction would.
 #include "bp_common.cuh"
 #include "guan_walker.cuh"
 #include "minors.cuh"
@@ -36,32 +43,21 @@ __device__ __forceinline__ cplx cshfl_xor(unsigned gmask, cplx a, int mask) {
     return r;
 }
 
-// 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset
-// (PIN: volatile, so that loads of the loop-invariant inner row stay inside the term loop instead of occupying registers)
-template <int OFF, bool PIN>
+// 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset: the C loads of a row
+// use ONE address register plus immediates (the compiler otherwise keeps a pointer per column)
+template <int OFF>
 __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
     double2 v;
-    if (PIN) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
-    else     asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
     return v;
-}
-// c[j] += sg * X2row[j] for the C columns of a lane (row given by its shared-window address)
-template <int C, bool PIN, int J = 0>
-__device__ __forceinline__ void k3_row_update(unsigned row, double sg, double (&cr)[C], double (&ci)[C]) {
-    if constexpr (J < C) {
-        const double2 a = lds_f64x2<J * (int)sizeof(double2), PIN>(row);
-        cr[J] = fma(sg, a.x, cr[J]);
-        ci[J] = fma(sg, a.y, ci[J]);
-        k3_row_update<C, PIN, J + 1>(row, sg, cr, ci);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Product engine 1: balanced product tree.  All C leave-one-out products of a term from an upward pass (node products,
+// Balanced product tree.  All C leave-one-out products of a term from an upward pass (node products,
 // C - 1 complex multiplies, depth ceil(log2 C)) and a downward pass (outside(child) = outside(parent) x sibling, the
 // leaf level fused into the accumulators): the same ~3C complex multiplies as prefix x suffix scans, but the dependency
-// depth is 2 log2 C instead of C and up to C / 2 multiplies are independent, so ONE warp keeps the FP64 pipe fed and a
-// lane can own all k <= 24 columns of a step (no shuffles, no butterfly multiplies).
+// depth is 2 log2 C instead of C and up to C / 2 multiplies are independent, and a lane can own up to 17 columns
+// (no shuffles, no butterfly multiplies for k <= 17).
 // node[MID] holds the product of the columns [LO, HI) with MID = (LO + HI) / 2 -- every internal node of the split tree
 // has its own MID in 1 .. C-1, so the indices are compile-time constants and the nodes live in registers.
 // ---------------------------------------------------------------------------------------------
@@ -107,14 +103,6 @@ __device__ __forceinline__ void k3_tree_down_real(double w, const double (&cr)[C
     }
 }
 
-// dynamic shared memory carve-up (bytes)
-__host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C, int threads) {
-    size_t x2 = (size_t)rows * W * sizeof(double2);
-    size_t red = (size_t)threads * C * sizeof(double2);
-    size_t dig = (size_t)rows * threads;
-    return ((x2 > red ? x2 : red) + dig + 15) / 16 * 16 + 16;
-}
-
 // Number of chunk blocks that actually work on a sample whose walk has `terms` terms: about
 // K3_TERMS_PER_GROUP terms per lane group, at most the launched `chunks`.  Bunched outputs shrink the
 // walk by orders of magnitude, so the grid is sized for the collision-free worst case and blocks beyond
@@ -127,19 +115,6 @@ __host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C, int thre
 // three of its own four warps.
 #define K3_WARP_THREADS 32
 #define K3_WARP_PMAX 128
-// tree engine: register budgets (blocks of 128 threads per SM) and the widest lane that keeps the inner row in registers
-#ifndef K3_TREE_MINB4_MAX_C
-#define K3_TREE_MINB4_MAX_C 5
-#endif
-#ifndef K3_TREE_MINB3_MAX_C
-#define K3_TREE_MINB3_MAX_C 8
-#endif
-#ifndef K3_TREE_MINB3_MAX_C1
-#define K3_TREE_MINB3_MAX_C1 11
-#endif
-#ifndef K3_TREE_REGROW_MAX_C
-#define K3_TREE_REGROW_MAX_C 8
-#endif
 struct __align__(16) K3Step { double blow; int off; int pad; };
 __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int chunks, unsigned long long per_block) {
     unsigned long long a = (terms + per_block - 1) / per_block;
@@ -148,33 +123,62 @@ __host__ __device__ inline int k3_active_chunks(unsigned long long terms, int ch
     return (int)a;
 }
 
-template <int LPG, int C, int THREADS, int ENG>
+// ---------------------------------------------------------------------------------------------
+// The term loop is ONE uniform loop.  The walk of a lane group is a sequence of PERIODS of P = prod_{v <= a_low} (lim_v + 1) terms;
+// inside a period every term does the same straight-line work -- fetch the 16-byte step entry of the next position, evaluate
+// the term (product tree), ADD the signed row of the digit that changes (the shared-memory image holds +2U rows, -2U rows and
+// a zero row, so a step is C complex additions from one address: no sign logic, no multiplication) -- and the branchy part
+// (the Guan step of the digits above the table, the reversal of the table direction) runs once per period in an outer loop.
+// Sentinel entries (weight 0, zero row) beyond both table ends make the last term of a period the same code as the others.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t k3_smem_bytes(int rows, int W, int C, int threads) {
+    size_t x2 = (size_t)(2 * rows + 1) * W * sizeof(double2);
+    size_t red = (size_t)threads * C * sizeof(double2);
+    size_t dig = (size_t)rows * threads;
+    return ((x2 > red ? x2 : red) + dig + 15) / 16 * 16 + 16;
+}
+// c[j] += row[j] for the C columns of a lane (row given by its shared-window address)
+template <int C, int J = 0>
+__device__ __forceinline__ void k3_row_add(unsigned row, double (&cr)[C], double (&ci)[C]) {
+    if constexpr (J < C) {
+        const double2 a = lds_f64x2<J * (int)sizeof(double2)>(row);
+        cr[J] += a.x;
+        ci[J] += a.y;
+        k3_row_add<C, J + 1>(row, cr, ci);
+    }
+}
+// resident 128-thread blocks per SM by column count (register caps 128 / 168 / 255): the widest lanes that compile without
+// spills under each cap (C = 6: 124 registers, C = 10: 162)
+#ifndef K3_MINB4_MAX_C
+#define K3_MINB4_MAX_C 6
+#endif
+#ifndef K3_MINB3_MAX_C
+#define K3_MINB3_MAX_C 10
+#endif
+template <int LPG, int C, int THREADS>
 struct K3Cfg {
-    // same register budget per thread for both block sizes
-    // (tree engine: the widest lanes that compile without spills under the 128- and 168-register caps)
-    static constexpr int MINB_128 = (ENG == 0) ? ((C <= 5) ? 4 : (C <= 8) ? 3 : 2)
-                                               : ((C <= K3_TREE_MINB4_MAX_C) ? 4 : (C <= (LPG == 1 ? K3_TREE_MINB3_MAX_C1 : K3_TREE_MINB3_MAX_C)) ? 3 : 2);
+    static constexpr int MINB_128 = (C <= K3_MINB4_MAX_C) ? 4 : (C <= K3_MINB3_MAX_C) ? 3 : 2;
     static constexpr int MINB = (MINB_128 * GW_THREADS / THREADS) < 1 ? 1 : (MINB_128 * GW_THREADS / THREADS);
     static constexpr int PMAX = (THREADS >= GW_THREADS) ? K3_PMAX : K3_WARP_PMAX;
-    // row of the inner digit: in registers (4C of them) or re-read from shared memory at every sweep step
-    static constexpr bool REGROW = (ENG == 0) || (C <= K3_TREE_REGROW_MAX_C);
 };
 
-// grid = (chunks, launch slots).  order: NULL (slot = sample) or [slots] sample of every launch slot.
-// occ_s / occ_t: [samples][m] uint8 occupations (current input with the newly added particle; outputs
-// sampled so far).  partials: [slots][chunks][LPG*C][4] double-double partial sums.
-template <int LPG, int C, int THREADS, int ENG>
-__global__ void __launch_bounds__(THREADS, K3Cfg<LPG, C, THREADS, ENG>::MINB)
+template <int LPG, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS, K3Cfg<LPG, C, THREADS>::MINB)
 k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const unsigned char *__restrict__ occ_s,
-                 const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, const int *__restrict__ order,
-                 int step, double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
+                  const unsigned char *__restrict__ occ_t, const int *__restrict__ steps_total, const int *__restrict__ order,
+                  int step, double *__restrict__ partials, unsigned long long *__restrict__ terms_out, unsigned long long per_block) {
     constexpr int W = LPG * C;
     constexpr int GROUPS = THREADS / LPG;
-    constexpr int PMAX = K3Cfg<LPG, C, THREADS, ENG>::PMAX;
-    constexpr bool REGROW = K3Cfg<LPG, C, THREADS, ENG>::REGROW;
+    constexpr int PMAX = K3Cfg<LPG, C, THREADS>::PMAX;
+    constexpr int ROWBYTES = W * (int)sizeof(double2);
     extern __shared__ __align__(16) unsigned char k3_smem[];
     __shared__ GuanItem item;
     __shared__ short col_mode[W];
+    // step tables, indexed by the DESTINATION position p + 1 inside a period: binomial product of the table digits at p and
+    // the byte offset of the signed row that leads there (fwd: from p - 1, bwd: from p + 1); entries 0 and P + 1 are sentinels
+    __shared__ K3Step fwd[PMAX + 2], bwd[PMAX + 2];
+    __shared__ int low_digits;                 // digits 0 .. low_digits are driven by the table
+    __shared__ unsigned period;                // P = prod_{v <= low_digits} (lim_v + 1): terms per table period
 
     const int slot = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int sample = order ? order[slot] : slot;
@@ -183,18 +187,8 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     if (steps_total && step >= steps_total[sample]) return;   // uniform-loss variant: this sample is complete
 
     const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
-    __shared__ double bin0[BP_MAX_N + 2];      // weight table of the inner digit: C(w_0, r) (x top weight if it is the only digit)
-    // step tables of the low digits, indexed by the DESTINATION position p inside a period: binomial product of the
-    // low digits at p plus the transition that leads there (row byte offset of the changed digit, bit 0 = digit went
-    // up); fwd: from p - 1, bwd: from p + 1 (reflected periods).  One 16-byte load per row step.
-    __shared__ K3Step fwd[PMAX], bwd[PMAX];
-    __shared__ int low_digits;                 // digits 1 .. low_digits are driven by the table
-    __shared__ unsigned period;                // P = prod_{v=1..low_digits} (lim_v + 1): rows per table period
     if (threadIdx.x == 0) {
         guan_item_build(item, t, m, /*inner_first=*/true);
-        if (item.D > 0)
-            for (int r = 0; r <= (int)item.lim[0]; ++r)
-                bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
     } else if (threadIdx.x == (THREADS > 32 ? 32 : 1)) {   // a second warp (lane, in one-warp blocks) expands the input columns meanwhile
         int c = 0;
         for (int v = 0; v < m; ++v)
@@ -206,8 +200,9 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     const int active = k3_active_chunks(item.terms, chunks, per_block);
     if (chunk == 0 && threadIdx.x == 0) terms_out[sample] = item.terms;
     if (chunk >= active) return;
+    // shared-memory image: rows [0, D) = +2 U[mode_v][cols], rows [D, 2D) = -2 U[mode_v][cols], row 2D = 0
     double2 *X2 = reinterpret_cast<double2 *>(k3_smem);
-    size_t x2_bytes = (size_t)D * W * sizeof(double2), red_bytes = (size_t)THREADS * C * sizeof(double2);
+    size_t x2_bytes = (size_t)(2 * D + 1) * W * sizeof(double2), red_bytes = (size_t)THREADS * C * sizeof(double2);
     unsigned char *rdig = k3_smem + ((x2_bytes > red_bytes ? x2_bytes : red_bytes) + 15) / 16 * 16;
     const double2 *U2 = reinterpret_cast<const double2 *>(U);
     for (int e = threadIdx.x; e < D * W; e += THREADS) {
@@ -216,22 +211,19 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         double2 x = make_double2(0.0, 0.0);
         if (cm >= 0) { const double2 u = U2[(int)item.mode[v] * m + cm]; x = make_double2(2.0 * u.x, 2.0 * u.y); }
         X2[e] = x;
+        X2[D * W + e] = make_double2(-x.x, -x.y);
     }
-    // The walk is organised in ROWS: one row = the L0 + 1 terms that differ only in digit 0 (swept up
-    // on even rows, down on odd rows: reflected code); rows are indexed by the sub-walk over digits
-    // 1 .. D-1.  A lane group owns a contiguous range of rows that is a multiple of the PERIOD of the
-    // low digits 1 .. low_digits; inside a period the step sequence is the same for every group, so it
-    // comes from a table built once per block (reflection: odd periods run it backwards).  Only the
-    // carry into the digits above (once per period) uses the generic Guan stepper.
-    const int L0 = item.lim[0];
-    const unsigned long long rows = item.terms / (unsigned long long)(L0 + 1);
+    for (int c = threadIdx.x; c < W; c += THREADS) X2[2 * D * W + c] = make_double2(0.0, 0.0);
+    const unsigned long long terms = item.terms;
     const unsigned long long ngroups = (unsigned long long)active * GROUPS;
     if (threadIdx.x == 0) {
-        unsigned long long raw = (rows + ngroups - 1) / ngroups, P = 1;
-        int a = 0;
-        for (int v = 1; v < D; ++v) {
+        // table digits: digit 0 always (work is dealt out in whole sweeps of it), further digits while a lane group still
+        // gets ~16 periods (balance: group ranges differ by at most one period) and the table fits
+        unsigned long long raw = (terms + ngroups - 1) / ngroups, P = 1;
+        int a = -1;
+        for (int v = 0; v < D; ++v) {
             const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
-            if (nxt * 16 > raw || nxt > (unsigned long long)PMAX) break;
+            if (v > 0 && (nxt * 16 > raw || nxt > (unsigned long long)PMAX)) break;
             P = nxt; a = v;
         }
         period = (unsigned)P;
@@ -241,11 +233,11 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     const unsigned P = period;
     const int a_low = low_digits;
     for (unsigned p = threadIdx.x; p < P; p += THREADS) {
-        // digits of position p and p - 1 of the reflected code over digits 1 .. a_low
+        // digits of position p and p - 1 of the reflected code over digits 0 .. a_low
         double bprod = 1.0;
         unsigned q = p, qm = p ? p - 1 : 0;
         int chg = 0, up = 0;
-        for (int v = 1; v <= a_low; ++v) {
+        for (int v = 0; v <= a_low; ++v) {
             const unsigned R = (unsigned)item.lim[v] + 1u;
             unsigned d = q % R; q /= R;
             unsigned dm = qm % R; qm /= R;
@@ -256,64 +248,60 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             if (v == D - 1) c *= gw_top_weight(item, rv);
             bprod *= c;
         }
-        const int rowbytes = W * (int)sizeof(double2);
-        fwd[p].blow = bprod; fwd[p].off = chg * rowbytes | up; fwd[p].pad = 0;
-        bwd[p].blow = bprod;
-        if (p == P - 1) { bwd[p].off = 0; bwd[p].pad = 0; }
-        if (p) { bwd[p - 1].off = chg * rowbytes | (up ^ 1); bwd[p - 1].pad = 0; }
+        // a digit that goes UP lowers its coefficient t - 2 rho by 2: the negated row
+        const int zero_row = 2 * D * ROWBYTES;
+        fwd[p + 1].blow = bprod; fwd[p + 1].off = p ? (chg + (up ? D : 0)) * ROWBYTES : zero_row; fwd[p + 1].pad = 0;
+        bwd[p + 1].blow = bprod;
+        if (p == P - 1) { bwd[p + 1].off = zero_row; bwd[p + 1].pad = 0; }
+        if (p) { bwd[p].off = (chg + (up ? 0 : D)) * ROWBYTES; bwd[p].pad = 0; }
+        if (p == 0) {   // sentinels: the step "beyond the end" of a period adds the zero row and carries weight 0
+            fwd[P + 1].blow = 0.0; fwd[P + 1].off = zero_row; fwd[P + 1].pad = 0;
+            bwd[0].blow = 0.0; bwd[0].off = zero_row; bwd[0].pad = 0;
+        }
     }
     __syncthreads();
 
     const int lane_in_group = threadIdx.x % LPG, group = threadIdx.x / LPG;
     // whole periods are dealt out to the lane groups; counts differ by at most one period
-    const unsigned long long nper = rows / P;                     // rows is a multiple of P
+    const unsigned long long nper = terms / P;                    // terms is a multiple of P
     const unsigned long long gidx = (unsigned long long)chunk * GROUPS + group;
     const unsigned long long pbase = nper / ngroups, prem = nper % ngroups;
-    const unsigned long long my_periods = pbase + (gidx < prem ? 1ull : 0ull);
-    const unsigned long long row_start = (gidx * pbase + (gidx < prem ? gidx : prem)) * P;
-    const unsigned long long rspan = my_periods * P;
-    // Trip counts are made WARP-uniform: the first group of a warp has the most periods (counts never grow with
-    // gidx); groups that own one period less run it as a dummy (weight 0, no stepping).  The butterfly can then
-    // use full-mask shuffles -- a per-group mask makes the compiler guard every shuffle with MATCH.ANY / VOTE /
-    // BRA.DIV, which cost 16 % of all issue-stall samples in the first version (profiles/r01_k3_n24_ncu_summary.txt).
+    const unsigned long long my_periods64 = pbase + (gidx < prem ? 1ull : 0ull);
+    const unsigned long long hi0 = gidx * pbase + (gidx < prem ? gidx : prem);   // first period of this group
+    // Trip counts are WARP-uniform (full-mask shuffles in the term loop): the first group of a warp has the most periods
+    // (counts never grow with gidx); a group that owns one period less runs it with weight 0.
     const unsigned long long gidx_w = (unsigned long long)chunk * GROUPS + (threadIdx.x & ~31u) / LPG;
-    // (per-group row counts fit 32 bits: at most 2^39 terms over >= 16 groups x active chunks, see bp_k3_chunks)
-    const unsigned warp_rows = (unsigned)((pbase + (gidx_w < prem ? 1ull : 0ull)) * P);
-    const unsigned my_rows = (unsigned)rspan;
+    const unsigned warp_periods = (unsigned)(pbase + (gidx_w < prem ? 1ull : 0ull));
+    const unsigned my_periods = (unsigned)my_periods64;
     const int col0 = lane_in_group * C;
 
     double ar[C], ai[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) { ar[j] = 0.0; ai[j] = 0.0; }
 
-    if (warp_rows > 0) {
+    if (warp_periods > 0) {
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
         st.dirmask = 0ull; st.binom = 0.0;
         const bool mine = my_periods > 0;
-        const unsigned long long hi0 = row_start / P;       // row_start is a multiple of P
         if (mine) guan_seek<THREADS>(item, hi0, r, st, /*v0=*/a_low + 1);      // digits above the table
-        int pos = (hi0 & 1ull) ? (int)P - 1 : 0;            // position inside the period (reflected)
+        int pos = (hi0 & 1ull) ? (int)P - 1 : 0;            // position inside the period (odd periods run backwards: reflected code)
         int pdir = (hi0 & 1ull) ? -1 : 1;
-        unsigned off = 0;                                    // rows done in the current period
-        int r0 = (row_start & 1ull) ? L0 : 0;               // reflected: odd rows sweep digit 0 downwards
-        int dir0 = (row_start & 1ull) ? -1 : 1;
-        double cr[C], ci[C], x0r[REGROW ? C : 1], x0i[REGROW ? C : 1];
+        double cr[C], ci[C];
 #pragma unroll
         for (int j = 0; j < C; ++j) { cr[j] = 0.0; ci[j] = 0.0; }
-        int par = r0;                                        // parity of sum(rho) -> sign of the term
+        int par = 0;                                         // parity of sum(rho) -> sign of the term
         if (mine) {
             unsigned q = (unsigned)pos;
 #pragma unroll 1
             for (int v = 0; v < D; ++v) {
                 int rv;
-                if (v == 0) rv = r0;
-                else if (v <= a_low) {
+                if (v <= a_low) {
                     const unsigned R = (unsigned)item.lim[v] + 1u;
                     const unsigned d = q % R; q /= R;
                     rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
                 } else rv = (int)r[v * THREADS];
-                if (v > 0) par += rv;
+                par += rv;
                 const double coef = 0.5 * (double)((int)item.mult[v] - 2 * rv);
                 const double2 *row = X2 + v * W + col0;
 #pragma unroll
@@ -325,168 +313,67 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             }
         }
 #pragma unroll
-        for (int j = 0; j < C; ++j) {
-            if constexpr (REGROW) {
-                const double2 a = X2[col0 + j];              // row of digit 0, kept in registers
-                x0r[j] = a.x; x0i[j] = a.y;
-            }
-            if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1
-        }
-        double sgn = (par & 1) ? -1.0 : 1.0;
-        double bout = mine ? st.binom * fwd[pos].blow : 0.0;    // binomial product of digits 1 .. D-1 (0: dummy rows)
-        const K3Step *tab = (pdir > 0) ? fwd : bwd;
-        // shared-window address of this lane's first column; kept opaque so that the row loads below use ONE address
-        // register plus immediates (the compiler otherwise hoists a separate pointer per column and spills)
+        for (int j = 0; j < C; ++j)
+            if (col_mode[col0 + j] < 0) { cr[j] = 1.0; ci[j] = 0.0; }   // padding column: constant 1 (its rows are zero)
+        // sign of the term x binomial product of the digits above the table; the sign flips with every term
+        double bsgn = mine ? ((par & 1) ? -st.binom : st.binom) : 0.0;
+        // shared-window addresses: this lane's first column of the image, and the two tables
         unsigned x2c0 = (unsigned)__cvta_generic_to_shared(X2 + col0);
         asm volatile("" : "+r"(x2c0));
-        double w0 = bin0[r0];                                // weight of digit 0, fetched one term ahead
+        const K3Step *tab = (pdir > 0) ? fwd : bwd;
+        double blow = fwd[pos + 1].blow;
 
-        constexpr int H = (C >= 6) ? C / 2 : C;             // columns [0, H) and [H, C) form two independent chains
 #pragma unroll 1
-        for (unsigned q = 0;;) {
-            // ---- plan the step to the next row now, so that its table / digit loads overlap the sweep below
-            const bool have_next = q + 1 < warp_rows;
-            int off_next = 0;                                // row byte offset of the digit that changes | went up
-            double blow_next = 0.0;                          // dummy rows: weight 0 (and sg_next = 0: c stays)
-            const bool real_next = q + 1 < my_rows;
-            if (real_next) {
-                if (++off < P) {
-                    // table step of the low digits (same for every group of the block)
-                    pos += pdir;
-                    const K3Step e = tab[pos];
-                    off_next = e.off;
-                    blow_next = e.blow;                      // multiplied by st.binom after the sweep: hides the load
+        for (unsigned per = 0;;) {
+#pragma unroll 1
+            for (unsigned i = 0; i < P; ++i) {
+                // step entry of the NEXT position, fetched before the term so that its latency hides behind the products
+                pos += pdir;
+                const K3Step e = tab[pos + 1];
+                const double w = bsgn * blow;
+                cplx node[C];
+                if constexpr (LPG == 1) {
+                    k3_tree_up<C, 0, C, false>(cr, ci, node);
+                    k3_tree_down_real<C>(w, cr, ci, node, ar, ai);
                 } else {
-                    // period boundary: one Guan step of the digits above the table; the low digits stay and reverse
-                    int delta;
-                    const int v = guan_step<THREADS>(item, r, st, delta, /*v0=*/a_low + 1);
-                    off_next = v * (W * (int)sizeof(double2)) | (delta > 0 ? 1 : 0);
-                    off = 0;
-                    pdir = -pdir;
-                    tab = (pdir > 0) ? fwd : bwd;
-                    blow_next = fwd[pos].blow;
-                }
-            }
-            const double sg_next = real_next ? ((off_next & 1) ? -1.0 : 1.0) : 0.0;   // c -= 2 * delta * X[v]
-            const unsigned row_next = x2c0 + (unsigned)(off_next & ~1);
-            // ---- inner sweep over digit 0: L0 + 1 terms, no stepping logic, no row loads
-#pragma unroll 1
-            for (int step = 0;; ++step) {
-                const double w = sgn * bout * w0;
-                bool last;
-                if constexpr (ENG == 0) {
-                    // prefix products over this lane's columns, one chain per half
-                    cplx pre[C];
-                    pre[0].re = 1.0; pre[0].im = 0.0;
-                    if (H > 1) { pre[1].re = cr[0]; pre[1].im = ci[0]; }
-    #pragma unroll
-                    for (int j = 2; j < H; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
-                    cplx totA, totB = {1.0, 0.0};
-                    if (H > 1) { cplx cl = {cr[H - 1], ci[H - 1]}; totA = cmul(pre[H - 1], cl); }
-                    else       { totA.re = cr[0]; totA.im = ci[0]; }
-                    if (H < C) {
-                        pre[H].re = 1.0; pre[H].im = 0.0;
-                        if (C - H > 1) { pre[H + 1].re = cr[H]; pre[H + 1].im = ci[H]; }
-    #pragma unroll
-                        for (int j = H + 2; j < C; ++j) { cplx cj = {cr[j - 1], ci[j - 1]}; pre[j] = cmul(pre[j - 1], cj); }
-                        if (C - H > 1) { cplx cl = {cr[C - 1], ci[C - 1]}; totB = cmul(pre[C - 1], cl); }
-                        else           { totB.re = cr[C - 1]; totB.im = ci[C - 1]; }
-                    }
-                    // product of the other lanes' totals (xor butterfly inside the group)
-                    cplx oth = {1.0, 0.0};
-                    if (LPG > 1) {
-                        cplx all = (H < C) ? cmul(totA, totB) : totA;
-    #pragma unroll
-                        for (int mask = 1; mask < LPG; mask <<= 1) {
-                            const cplx x = cshfl_xor(0xffffffffu, all, mask);
-                            oth = (mask == 1) ? x : cmul(oth, x);
-                            if ((mask << 1) < LPG) all = cmul(all, x);
-                        }
+                    k3_tree_up<C, 0, C, true>(cr, ci, node);
+                    cplx all = k3_tree_val<C, 0, C>(cr, ci, node), oth = {1.0, 0.0};
+#pragma unroll
+                    for (int mask = 1; mask < LPG; mask <<= 1) {
+                        const cplx x = cshfl_xor(0xffffffffu, all, mask);
+                        oth = (mask == 1) ? x : cmul(oth, x);
+                        if ((mask << 1) < LPG) all = cmul(all, x);
                     }
                     cplx seed = {w * oth.re, w * oth.im};
-                    // next value of digit 0 (its weight is needed one term ahead)
-                    last = (step == L0);
-                    if (!last) r0 += dir0;
-                    w0 = bin0[r0];
-                    // suffix passes: leave-one-out products, accumulated; the two halves seed each other's totals
-                    if (H < C) {
-                        cplx sufB = cmul(seed, totA);
-    #pragma unroll
-                        for (int j = C - 1; j >= H; --j) {
-                            if (j == H) { ar[H] += sufB.re; ai[H] += sufB.im; }
-                            else {
-                                cmul_acc(ar[j], ai[j], pre[j], sufB);
-                                cplx cj = {cr[j], ci[j]};
-                                sufB = cmul(sufB, cj);
-                            }
-                        }
-                    }
-                    cplx sufA = (H < C) ? cmul(seed, totB) : seed;
-    #pragma unroll
-                    for (int j = H - 1; j >= 0; --j) {
-                        if (j == 0) { ar[0] += sufA.re; ai[0] += sufA.im; }
-                        else {
-                            cmul_acc(ar[j], ai[j], pre[j], sufA);          // acc_j += prefix_j * suffix_j, fused
-                            cplx cj = {cr[j], ci[j]};
-                            sufA = cmul(sufA, cj);
-                        }
-                    }
-                } else {
-                    // balanced product tree (see k3_tree_up / k3_tree_down)
-                    cplx node[C];
-                    bool last_t;
-                    if constexpr (LPG == 1) {
-                        k3_tree_up<C, 0, C, false>(cr, ci, node);
-                        last_t = (step == L0);
-                        if (!last_t) r0 += dir0;
-                        w0 = bin0[r0];
-                        k3_tree_down_real<C>(w, cr, ci, node, ar, ai);
-                    } else {
-                        k3_tree_up<C, 0, C, true>(cr, ci, node);
-                        cplx all = k3_tree_val<C, 0, C>(cr, ci, node), oth = {1.0, 0.0};
-#pragma unroll
-                        for (int mask = 1; mask < LPG; mask <<= 1) {
-                            const cplx x = cshfl_xor(0xffffffffu, all, mask);
-                            oth = (mask == 1) ? x : cmul(oth, x);
-                            if ((mask << 1) < LPG) all = cmul(all, x);
-                        }
-                        last_t = (step == L0);
-                        if (!last_t) r0 += dir0;
-                        w0 = bin0[r0];
-                        cplx seed = {w * oth.re, w * oth.im};
-                        k3_tree_down<C, 0, C>(seed, cr, ci, node, ar, ai);
-                    }
-                    last = last_t;
+                    k3_tree_down<C, 0, C>(seed, cr, ci, node, ar, ai);
                 }
-                if (last) break;
-                // c -= 2 * dir0 * X[0]
-                sgn = -sgn;
-                const double sg = (dir0 > 0) ? -1.0 : 1.0;
-                if constexpr (REGROW) {
-#pragma unroll
-                    for (int j = 0; j < C; ++j) { cr[j] = fma(sg, x0r[j], cr[j]); ci[j] = fma(sg, x0i[j], ci[j]); }
-                } else {
-                    k3_row_update<C, true>(x2c0, sg, cr, ci);
-                }
+                bsgn = -bsgn;
+                blow = e.blow;
+                k3_row_add<C>(x2c0 + (unsigned)e.off, cr, ci);
             }
-            dir0 = -dir0;
-            // ---- next row
-            if (!have_next) break;
-            ++q;
-            sgn = -sgn;
-            bout = st.binom * blow_next;
-            k3_row_update<C, false>(row_next, sg_next, cr, ci);
+            // ---- period boundary: one Guan step of the digits above the table; the table digits stay and reverse
+            if (++per >= warp_periods) break;
+            pos -= pdir;                                     // the sentinel step overshot by one
+            pdir = -pdir;
+            tab = (pdir > 0) ? fwd : bwd;
+            blow = fwd[pos + 1].blow;
+            if (per < my_periods) {
+                int delta;
+                const int v = guan_step<THREADS>(item, r, st, delta, /*v0=*/a_low + 1);
+                k3_row_add<C>(x2c0 + (unsigned)((v + (delta > 0 ? D : 0)) * ROWBYTES), cr, ci);
+                bsgn = (bsgn < 0.0) ? -st.binom : st.binom;
+            } else {
+                bsgn = 0.0;                                  // dummy period of a group that owns one period less
+            }
         }
     }
 
     // ---- block reduction: column (lane_in_group, j) over the GROUPS groups, double-double
-    __syncthreads();   // X2 is dead from here on; its storage is reused
+    __syncthreads();   // the image is dead from here on; its storage is reused
     double2 *red = reinterpret_cast<double2 *>(k3_smem);   // [W][GROUPS]
 #pragma unroll
     for (int j = 0; j < C; ++j) red[(col0 + j) * GROUPS + group] = make_double2(ar[j], ai[j]);
     __syncthreads();
-    // PARTS threads per column: each adds a contiguous slice of the groups (double-double, group order), thread 0 of
-    // the column then adds the PARTS partial sums in slice order -- a fixed summation order, GROUPS / PARTS deep
     static_assert(THREADS >= W, "one reduction thread per column");
     constexpr int PARTS = (THREADS / W) > 8 ? 8 : (THREADS / W);
     constexpr int SLICE = (GROUPS + PARTS - 1) / PARTS;
@@ -709,96 +596,54 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
 typedef void (*k3_fn)(const double *, size_t, int, const unsigned char *, const unsigned char *, const int *, const int *, int, double *, unsigned long long *, unsigned long long);
 
 struct K3Variant { k3_fn fn; int lpg, c, threads; };
-#define K3_MAX_C 12
-#define K3_WARP_MAX_C 8
 #define K3_WARP_DEFAULT_MAX_K 16
-static K3Variant g_k3[4][K3_MAX_C + 1];        // engine 0 (prefix x suffix scans): [log2 LPG][C], 128-thread blocks
-static K3Variant g_k3w[2][K3_WARP_MAX_C + 1];  // engine 0, one-warp blocks (LPG <= 2: k <= 16)
-// engine 1 (product tree): one lane owns all columns up to k = K3_TREE_MAX_C1, two (four) lanes share them beyond
-#define K3_TREE_MAX_C1 19   // widest lanes that compile without spills: 19 / 15 / 12 columns for 1 / 2 / 4 lanes per group
-#define K3_TREE_MAX_C2 15
-#define K3_TREE_WARP_MAX_C 16
-#define K3_TREE_MAX_C4 12
-static K3Variant g_k3t[3][K3_TREE_MAX_C1 + 1];     // [log2 LPG][C], 128-thread blocks
-static K3Variant g_k3tw[K3_TREE_WARP_MAX_C + 1];   // LPG = 1, one-warp blocks
+// one lane owns all columns up to k = K3_MAX_C1, two (four) lanes share them beyond: the widest lanes that compile without spills
+#define K3_MAX_C1 17
+#define K3_MAX_C2 15
+#define K3_MAX_C4 12
+#define K3_WARP_MAX_C 16
+static K3Variant g_k3[3][K3_MAX_C1 + 1];     // [log2 LPG][C], 128-thread blocks
+static K3Variant g_k3w[K3_WARP_MAX_C + 1];   // LPG = 1, one-warp blocks
 
-template <int LPG, int C>
-static void k3_reg(int lg) {
-    g_k3[lg][C] = K3Variant{k3_minors_kernel<LPG, C, GW_THREADS, 0>, LPG, C, GW_THREADS};
-    if constexpr (LPG <= 2 && C <= K3_WARP_MAX_C) g_k3w[lg][C] = K3Variant{k3_minors_kernel<LPG, C, K3_WARP_THREADS, 0>, LPG, C, K3_WARP_THREADS};
-}
-template <int LPG>
-static void k3_reg_all(int lg) {
-    k3_reg<LPG, 1>(lg); k3_reg<LPG, 2>(lg); k3_reg<LPG, 3>(lg); k3_reg<LPG, 4>(lg);
-    k3_reg<LPG, 5>(lg); k3_reg<LPG, 6>(lg); k3_reg<LPG, 7>(lg); k3_reg<LPG, 8>(lg);
-    k3_reg<LPG, 9>(lg); k3_reg<LPG, 10>(lg); k3_reg<LPG, 11>(lg); k3_reg<LPG, 12>(lg);
-}
 template <int C>
-static void k3_reg_tree() {
-    g_k3t[0][C] = K3Variant{k3_minors_kernel<1, C, GW_THREADS, 1>, 1, C, GW_THREADS};
-    if constexpr (C <= K3_TREE_WARP_MAX_C) g_k3tw[C] = K3Variant{k3_minors_kernel<1, C, K3_WARP_THREADS, 1>, 1, C, K3_WARP_THREADS};
-    if constexpr (C <= K3_TREE_MAX_C2 && C >= 5) g_k3t[1][C] = K3Variant{k3_minors_kernel<2, C, GW_THREADS, 1>, 2, C, GW_THREADS};
-    if constexpr (C <= K3_TREE_MAX_C4 && C >= 5) g_k3t[2][C] = K3Variant{k3_minors_kernel<4, C, GW_THREADS, 1>, 4, C, GW_THREADS};
-    if constexpr (C > 1) k3_reg_tree<C - 1>();
+static void k3_reg() {
+    g_k3[0][C] = K3Variant{k3_minors_kernel<1, C, GW_THREADS>, 1, C, GW_THREADS};
+    if constexpr (C <= K3_WARP_MAX_C) g_k3w[C] = K3Variant{k3_minors_kernel<1, C, K3_WARP_THREADS>, 1, C, K3_WARP_THREADS};
+    if constexpr (C <= K3_MAX_C2 && C >= 4) g_k3[1][C] = K3Variant{k3_minors_kernel<2, C, GW_THREADS>, 2, C, GW_THREADS};
+    if constexpr (C <= K3_MAX_C4 && C >= 4) g_k3[2][C] = K3Variant{k3_minors_kernel<4, C, GW_THREADS>, 4, C, GW_THREADS};
+    if constexpr (C > 1) k3_reg<C - 1>();
 }
 
-// Variant for k input columns.
-//   engine 1 (default): product tree; one lane per term stream with all k <= 19 columns, two lanes with ceil(k / 2) columns
-//     each for k = 20 .. 30, four lanes for k = 31 .. 48; one-warp blocks for the steps k <= K3_WARP_DEFAULT_MAX_K whose
-//     walk fits one block.
-//   engine 0 (BP_K3_ENGINE=0, kept for A/B measurements): smallest padded width LPG * C >= k with C <= max_c, preferring
-//     fewer lanes per group; max_c is 8, except k = 17 .. 24 where two lanes with up to 12 columns beat four with up to 6.
-// Tuning knobs, read once: BP_K3_ENGINE, BP_K3_MAX_C (engine 0: column limit for all k), BP_K3_WIDE_MIN_K (engine 0: first k
-// of the two-lane rule), BP_K3_WARP_MAX_K (0 = never one-warp blocks), BP_K3_TREE_MAX_C (engine 1: column limit per lane).
-#define K3_DEFAULT_MAX_C 8
+// Variant for k input columns: one lane per term stream with all k <= 17 columns, two lanes with ceil(k / 2) columns each for
+// k = 18 .. 30, four lanes for k = 31 .. 48; one-warp blocks for the steps k <= K3_WARP_DEFAULT_MAX_K whose walk fits one block.
+// Tuning knobs, read once: BP_K3_WARP_MAX_K (0 = never one-warp blocks), BP_K3_TREE_MAX_C (column limit per lane, >= 6).
 static K3Variant k3_pick(int k) {
-    static int forced_max_c = 0, warp_max_k = K3_WARP_DEFAULT_MAX_K, wide_min_k = 17, engine = 1, tree_max_c1 = K3_TREE_MAX_C1;
+    static int warp_max_k = K3_WARP_DEFAULT_MAX_K, max_c1 = K3_MAX_C1;
     static const bool ready = [] {   // thread-safe one-time registration (C++11 static initialisation)
 #ifdef K3_DEV_C   // development builds: a single instantiation (seconds to compile; for SASS inspection only)
-        g_k3t[0][K3_DEV_C] = K3Variant{k3_minors_kernel<K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS, K3_DEV_ENG>, K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS};
+        g_k3[0][K3_DEV_C] = K3Variant{k3_minors_kernel<K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS>, K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS};
 #else
-        k3_reg_all<1>(0); k3_reg_all<2>(1); k3_reg_all<4>(2); k3_reg_all<8>(3);
-        k3_reg_tree<K3_TREE_MAX_C1>();
+        k3_reg<K3_MAX_C1>();
 #endif
-        const char *e = getenv("BP_K3_MAX_C");
-        forced_max_c = e ? atoi(e) : 0;
-        if (forced_max_c > K3_MAX_C) forced_max_c = K3_MAX_C;
+        const char *e;
         if ((e = getenv("BP_K3_WARP_MAX_K"))) warp_max_k = atoi(e);
-        if ((e = getenv("BP_K3_WIDE_MIN_K"))) wide_min_k = atoi(e);
-        if ((e = getenv("BP_K3_ENGINE"))) engine = atoi(e) ? 1 : 0;
-        if ((e = getenv("BP_K3_TREE_MAX_C"))) tree_max_c1 = atoi(e);
-        if (tree_max_c1 > K3_TREE_MAX_C1) tree_max_c1 = K3_TREE_MAX_C1;
-        if (tree_max_c1 < 6) tree_max_c1 = 6;
+        if ((e = getenv("BP_K3_TREE_MAX_C"))) max_c1 = atoi(e);
+        if (max_c1 > K3_MAX_C1) max_c1 = K3_MAX_C1;
+        if (max_c1 < 6) max_c1 = 6;
         return true;
     }();
     (void)ready;
     K3Variant none = {nullptr, 0, 0, 0};
     if (k < 1) return none;
-    if (engine == 1) {
-        // fewest lanes per group whose column count fits the lane limit
-        for (int lg = 0; lg < 3; ++lg) {
-            const int lpg = 1 << lg, c = (k + lpg - 1) / lpg;
-            const int lim = lg == 0 ? tree_max_c1 : lg == 1 ? (tree_max_c1 < K3_TREE_MAX_C2 ? tree_max_c1 : K3_TREE_MAX_C2)
-                                                            : (tree_max_c1 < K3_TREE_MAX_C4 ? tree_max_c1 : K3_TREE_MAX_C4);
-            if (c > lim) continue;
-            if (lg == 0 && k <= warp_max_k && k <= K3_TREE_WARP_MAX_C) return g_k3tw[k];
-            if (g_k3t[lg][c].fn) return g_k3t[lg][c];
-        }
-        // beyond the tree variants: fall through to the scan engine's eight-lane layouts
+    // fewest lanes per group whose column count fits the lane limit
+    for (int lg = 0; lg < 3; ++lg) {
+        const int lpg = 1 << lg, c = (k + lpg - 1) / lpg;
+        const int lim = lg == 0 ? max_c1 : lg == 1 ? (max_c1 < K3_MAX_C2 ? max_c1 : K3_MAX_C2) : K3_MAX_C4;
+        if (c > lim) continue;
+        if (lg == 0 && k <= warp_max_k && k <= K3_WARP_MAX_C) return g_k3w[k];
+        if (g_k3[lg][c].fn) return g_k3[lg][c];
     }
-    const int wmax = warp_max_k > 2 * K3_WARP_MAX_C ? 2 * K3_WARP_MAX_C : warp_max_k;
-    int max_c = (k >= wide_min_k && k <= 24) ? K3_MAX_C : K3_DEFAULT_MAX_C;
-    if (forced_max_c >= 7) max_c = forced_max_c;
-    int best_lg = -1, best_c = 0, best_w = 1 << 30;
-    for (int lg = 0; lg < 4; ++lg) {
-        const int lpg = 1 << lg;
-        const int c = (k + lpg - 1) / lpg;
-        if (c > max_c) continue;
-        if (lpg * c < best_w) { best_w = lpg * c; best_lg = lg; best_c = c; }
-    }
-    if (best_lg < 0) return none;
-    if (k <= wmax && best_lg <= 1 && best_c <= K3_WARP_MAX_C) return g_k3w[best_lg][best_c];
-    return g_k3[best_lg][best_c];
+    return none;
 }
 
 int bp_k3_width(int k) { K3Variant v = k3_pick(k); return v.fn ? v.lpg * v.c : 0; }
@@ -859,7 +704,7 @@ int bp_k3_launch(bp_context *h, const double *dU, size_t u_stride, int m, const 
                  unsigned long long *d_terms) {
     if (k <= 1) return BP_OK;   // handled by the finish kernel
     K3Variant v = k3_pick(k);
-    if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= %d, got %d", 8 * K3_DEFAULT_MAX_C, k);
+    if (!v.fn) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k <= %d, got %d", 4 * K3_MAX_C4, k);
     if (k - 1 > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "minors kernel supports k - 1 <= %d, got k = %d", BP_MAX_N, k);
     if (samples > 65535) return bp_fail(h, BP_ERR_INVALID, "bp_k3_launch: at most 65535 samples per launch");
     const size_t smem = k3_smem_bytes(k - 1, v.lpg * v.c, v.c, v.threads);
