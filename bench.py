@@ -137,6 +137,27 @@ def reference_python_fixture():
         return None
 
 
+def reference_python_live(timeout_s=240):
+    """The UNMODIFIED Python reference timed on THIS host in this run: scripts/time_reference_python.py --bounded in a
+    subprocess against baseline/_ref (the reference installed by scripts/install_reference.sh; git-ignored, shipped with the
+    working tree).  Glynn at N = 14 / 16 / 18 on one core and over all cores, BASELINE config 1 as is.  About 25 s."""
+    ref = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "theboss")):
+        msg = "baseline/_ref is missing (scripts/install_reference.sh): the Python reference could NOT be timed on this host"
+        print("bench.py: " + msg, file=sys.stderr)
+        return {"error": msg}
+    try:
+        run = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "time_reference_python.py"), "--bounded"],
+                             env=dict(os.environ, THEBOSS_REFERENCE=ref, CUDA_VISIBLE_DEVICES=""), capture_output=True, text=True,
+                             timeout=timeout_s, cwd=REPO)
+        if run.returncode != 0:
+            raise RuntimeError(run.stderr[-400:])
+        return json.loads(run.stdout.strip().splitlines()[-1])
+    except Exception as e:   # noqa: BLE001
+        print(f"bench.py: timing the Python reference failed: {e!r}", file=sys.stderr)
+        return {"error": repr(e)}
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_port_sample(target_seconds=12.0):
     """Times the CPU oracle port (double precision, all host threads) on a bounded sample of the C4
@@ -183,7 +204,7 @@ def cpu_port_sample(target_seconds=12.0):
     s = 20
     t = run(s)
     while t < 0.5 and s < N_PHOTONS - 1:
-        s += 2
+        s = min(s + 2, N_PHOTONS - 1)             # never past the 2^(N-1) steps of the permanent
         t = run(s)
     # scale to the target duration
     grow = int(np.floor(np.log2(max(target_seconds / max(t, 1e-6), 1.0))))
@@ -277,27 +298,6 @@ def secondary_metrics(device):
         out["gccb_n20_m40"] = {"samples": 16384, "seconds": tg, "samples_per_s": 16384 / tg}
     except Exception as e:   # noqa: BLE001
         out["gccb_n24_m48"] = {"error": repr(e)}
-    try:   # C5 (i): uniform losses eta = 0.5, n=30, m=60
-        U, U_lossy, s = workloads.c5_lossy(30, 60)
-        S_n = 2000
-        t = best_of(lambda: h.gccb_simulate(U, s, S_n, eta=0.5, seed=5), reps=2)
-        out["c5_uniform_losses_n30_m60"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t}
-    except Exception as e:   # noqa: BLE001
-        out["c5_uniform_losses_n30_m60"] = {"error": repr(e)}
-    try:   # C5 (ii): non-uniform losses through the 2m-mode dilation, n=30, m=60 (bounded sample count: every sample
-           # costs up to 3.4e11 flops)
-        from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import prepare_interferometer_matrix_in_expanded_space
-        U, U_lossy, s = workloads.c5_lossy(30, 60)
-        big = np.ascontiguousarray(prepare_interferometer_matrix_in_expanded_space(U_lossy))
-        s_big = np.concatenate([s, np.zeros(60, dtype=np.int32)])
-        S_n = 64
-        t0 = time.perf_counter()
-        res = h.gccb_simulate(big, s_big, S_n, seed=5)
-        t = time.perf_counter() - t0
-        out["c5_nonuniform_losses_n30_m60"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t,
-                                               "mean_particles_detected": float(res[:, :60].sum(axis=1).mean())}
-    except Exception as e:   # noqa: BLE001
-        out["c5_nonuniform_losses_n30_m60"] = {"error": repr(e)}
     try:   # C1: GCC (version A), n=5, m=10, 1000 samples through the strategy class
         from theboss_b200.boson_sampling_utilities.permanent_calculators.glynn_gray_permanent_calculator import GlynnGrayPermanentCalculator
         from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy
@@ -314,8 +314,9 @@ def secondary_metrics(device):
 
 
 def sampling_algorithmic_flops(samples, seed=0):
-    """Algorithmic flops of the GCC-B runs that produced `samples` ((S, m) output occupations, n particles each):
-    sum over samples and steps k = 2 .. n of T_k * (22 k - 36), T_k = ceil(prod_j (t_j + 1) / 2) for the occupation t of
+    """Algorithmic flops of the GCC-B runs that produced `samples` ((S, m) output occupations; the particle number may differ
+    from sample to sample -- lossy runs): sum over samples and steps k = 2 .. n_sample of T_k * (22 k - 36),
+    T_k = ceil(prod_j (t_j + 1) / 2) for the occupation t of
     the k - 1 outputs drawn before step k (the count of the Glynn / Lemma-2 form the
     kernels evaluate, NOT the reference's 4x larger sub-Ryser sweep).  The order in which a sample's particles were drawn is
     not kept, but the chain-rule sequence of output modes is exchangeable (its joint pmf is |perm|^2 up to symmetric
@@ -323,22 +324,30 @@ def sampling_algorithmic_flops(samples, seed=0):
     one uniformly random order per sample gives an unbiased figure whose relative spread over thousands of samples is
     far below a percent (tests/test_host_logic.py checks it against the true draw order of the oracle's loop)."""
     samples = np.asarray(samples, dtype=np.int64)
-    S, m = samples.shape
-    n = int(samples[0].sum()) if S else 0
-    if S == 0 or n < 2:
+    if samples.ndim != 2 or samples.shape[0] == 0:
         return 0.0
-    if not (samples.sum(axis=1) == n).all():
-        raise ValueError("samples hold different particle numbers")
+    S, m = samples.shape
+    counts = samples.sum(axis=1)
+    n = int(counts.max())
+    if n < 2:
+        return 0.0
     rng = np.random.RandomState(seed)
-    modes = np.repeat(np.tile(np.arange(m), S), samples.reshape(-1)).reshape(S, n)       # particle list of every sample
-    order = np.argsort(rng.random_sample((S, n)), axis=1)
-    modes = np.take_along_axis(modes, order, axis=1)                                     # uniformly random draw order
+    # particle list of every sample, padded with -1 behind its own particles, in a uniformly random draw order
+    modes = np.full((S, n), -1, dtype=np.int64)
+    flat = np.repeat(np.tile(np.arange(m), S), samples.reshape(-1))
+    modes[np.arange(n)[None, :] < counts[:, None]] = flat          # row-major fill: sample i gets its own particles
+    # random keys (padding sorts last): positions < count hold a uniformly random permutation of the sample's particles
+    modes = np.take_along_axis(modes, np.argsort(np.where(modes >= 0, rng.random_sample((S, n)), 2.0), axis=1), axis=1)
     occupation = np.zeros((S, m), dtype=np.int64)
     rows = np.arange(S)
     flops = 0.0
     for k in range(2, n + 1):
-        occupation[rows, modes[:, k - 2]] += 1                                           # outputs drawn before step k
-        terms = (np.prod(occupation + 1, axis=1, dtype=np.float64) + 1) // 2
+        live = counts >= k - 1                                                           # samples that drew a (k-1)-th output
+        occupation[rows[live], modes[live, k - 2]] += 1                                  # outputs drawn before step k
+        step = counts >= k                                                               # samples that take step k
+        if not step.any():
+            break
+        terms = (np.prod(occupation[step] + 1, axis=1, dtype=np.float64) + 1) // 2
         flops += float(terms.sum()) * (22 * k - 36)
     return flops
 
@@ -347,7 +356,7 @@ def sampling_roofline(samples, ms, fp64_peak, world):
     """`roofline` object of the GCC-B sampling leg: algorithmic flops of the run (from its own outputs) per second of
     device time, against the FP64 probe of rank 0 times the number of ranks."""
     try:
-        total, n = int(samples.shape[0]), int(samples[0].sum())
+        total, n = int(samples.shape[0]), int(samples.sum(axis=1).max())
         flops = sampling_algorithmic_flops(samples)
         achieved = flops / (ms * 1e-3) / 1e12
         return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak * world, "unit": "TFLOP/s",
@@ -437,6 +446,127 @@ def gccb_sampling_leg(world, rank, local_rank, fp64_peak, per_rank=4096):
                     "input |1^24 0^24>; device time incl. H2D of U and D2H of the samples, max over ranks"}
 
 
+def c5_legs(world, rank, local_rank, fp64_peak):
+    """BASELINE configs[4]: lossy GCC sampling at n=30, m=60, sharded over the ranks (contiguous slices of one Philox-keyed
+    job, no traffic until the final gather).
+      (i)  uniform losses eta = 0.5: 10^4 samples in total at every N (strong scaling);
+      (ii) non-uniform losses (U diag(sqrt(eta_j)), eta = linspace(0.3, 0.9)) through the 120-mode dilation: 1250 samples per
+           rank (weak scaling) -- at 8 ranks that is the 10^4 samples of the config, at 1 rank it keeps the default run short
+           (a sample costs up to 3.4e11 flops).
+    Device time of the host-pointer call (H2D of the matrix, init / tape kernels, every K3 + finish launch, D2H of the samples),
+    max over ranks.  `identical_to_single_gpu`: rank 0 redraws samples of OTHER ranks' slices on its own GPU and compares."""
+    import torch
+    import torch.distributed as dist
+
+    from theboss_b200 import _native
+    from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import prepare_interferometer_matrix_in_expanded_space
+    from theboss_b200.distributed import gather_samples, shard_bounds
+
+    h = _native.default_handle(local_rank)
+    dev = f"cuda:{local_rank}"
+    U, U_lossy, s = workloads.c5_lossy(30, 60)
+    big = np.ascontiguousarray(prepare_interferometer_matrix_in_expanded_space(U_lossy))
+    s_big = np.concatenate([s, np.zeros(60, dtype=np.int32)])
+    out = {}
+    for name, matrix, state, eta, total, scaling in (
+            ("uniform_eta0.5", U, s, 0.5, 10_000, "strong"),
+            ("nonuniform_dilated", big, s_big, -1.0, 1250 * world, "weak")):
+        lo, hi = shard_bounds(total, world, rank)
+        h.gccb_simulate(matrix, state, min(hi - lo, 64), eta=eta, seed=2, first_sample=lo)      # warm-up (scratch allocation)
+        best_ms, local, launches = None, None, 0
+        for _ in range(2 if eta >= 0 else 1):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            l0 = h.launch_count()
+            h.timer_start()
+            local = h.gccb_simulate(matrix, state, hi - lo, eta=eta, seed=5, first_sample=lo)
+            ms = h.timer_stop()
+            launches = h.launch_count() - l0
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best_ms = float(t.item()) if best_ms is None else min(best_ms, float(t.item()))
+        everything = gather_samples(torch.from_numpy(local).to(dev)).cpu().numpy()
+        leg = {"samples": total, "scaling": scaling, "ms": best_ms, "samples_per_s": total / (best_ms * 1e-3), "gpu_launches": int(launches)}
+        if rank == 0:
+            counts = everything.sum(axis=1)
+            leg["particles_conserved"] = bool(everything.shape[0] == total and (counts == 30).all()) if eta < 0 else \
+                bool(everything.shape[0] == total and counts.max() <= 30 and abs(counts.mean() - 15.0) < 0.5)
+            leg["mean_particles_detected"] = float(everything[:, :60].sum(axis=1).mean())
+            # redraw on this GPU: everything for the cheap uniform run, a few samples from the far end for the dilated one
+            if eta >= 0:
+                again = h.gccb_simulate(matrix, state, total, eta=eta, seed=5, first_sample=0)
+                leg["identical_to_single_gpu"] = bool(np.array_equal(again, everything))
+            else:
+                again = h.gccb_simulate(matrix, state, 4, eta=eta, seed=5, first_sample=total - 4)
+                leg["identical_to_single_gpu"] = bool(np.array_equal(again, everything[total - 4:]))
+                leg["identity_checked_on"] = "the last 4 samples of the job (drawn by the last rank)"
+            leg["roofline"] = sampling_roofline(everything, best_ms, fp64_peak, world)
+        out[name] = leg
+    return out
+
+
+def c2_leg(world, rank, local_rank, fp64_peak):
+    """BASELINE configs[1]: 10^4 batched n=20 permanents with repeated rows and columns (m=40), items sharded over the ranks
+    (strong scaling), through the host-pointer entry point bp_perm_batched; device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from theboss_b200 import _native
+    from theboss_b200.distributed import shard_bounds
+
+    h = _native.default_handle(local_rank)
+    dev = f"cuda:{local_rank}"
+    items, n = 10_000, 20
+    U, S, T = workloads.c2_batch(n, 40, items)
+    lo, hi = shard_bounds(items, world, rank)
+    h.perm_batched(U, S[lo:hi], T[lo:hi])
+    best_ms, local, launches = None, None, 0
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = h.launch_count()
+        h.timer_start()
+        local = h.perm_batched(U, S[lo:hi], T[lo:hi])
+        ms = h.timer_stop()
+        launches = h.launch_count() - l0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best_ms = float(t.item()) if best_ms is None else min(best_ms, float(t.item()))
+    # final gather of the results (16 bytes per item)
+    mine = torch.zeros(items, dtype=torch.complex128, device=dev)
+    mine[lo:hi] = torch.from_numpy(local).to(dev)
+    if world > 1:
+        re = torch.view_as_real(mine).contiguous()
+        dist.all_reduce(re)
+        mine = torch.view_as_complex(re)
+    everything = mine.cpu().numpy()
+    cs = np.prod(S.astype(np.float64) + 1, axis=1)
+    ct = np.prod(T.astype(np.float64) + 1, axis=1)
+    terms = float((np.ceil(np.minimum(cs, ct) / 2)).sum())
+    d = np.where(cs <= ct, (T > 0).sum(axis=1), (S > 0).sum(axis=1))     # distinct modes on the product side
+    flops = float((np.ceil(np.minimum(cs, ct) / 2) * (2 * d + 6 * (n - 1) + 4)).sum())
+    achieved = flops / (best_ms * 1e-3) / 1e12
+    leg = {"items": items, "scaling": "strong", "ms": best_ms, "permanents_per_s": items / (best_ms * 1e-3), "gpu_launches": int(launches),
+           "guan_terms": terms,
+           "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak * world, "unit": "TFLOP/s",
+                        "frac": achieved / (fp64_peak * world), "traffic": None, "kernel": "k2_perm_kernel<20>",
+                        "algorithmic_flops": flops,
+                        "note": "flops = sum over items of ceil(min(prod(s+1), prod(t+1)) / 2) * (2 d + 6 (n - 1) + 4), SURVEY.md section 8(d)"}}
+    if rank == 0:
+        # correctness gate: the first items of the batch are the ones the unmodified reference was run on
+        # (tests/golden/reference_large.json, Chin-Huh calculator)
+        with open(os.path.join(REPO, "tests", "golden", "reference_large.json")) as f:
+            ref = json.load(f)["c2"]["chin_huh"]
+        worst = max(abs(everything[int(i)] - complex(re, im)) / abs(complex(re, im)) for i, (re, im) in ref.items())
+        leg["max_rel_err_vs_reference_outputs"] = float(worst)
+        leg["matches_reference_outputs_1e-10"] = bool(worst <= 1e-10)
+    return leg
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure
     Python (~2.3 h per n=30 permanent) and /root/reference does not exist on the
@@ -458,7 +588,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
-                         "reference_python": reference_python_fixture()},
+                         "reference_python": reference_python_fixture(), "reference_python_live": reference_python_live()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "ms_per_step is the time one full n=30 permanent would take on the host cores (extrapolated from the bounded sample)",
@@ -559,6 +689,16 @@ def run_native(args):
     except Exception as e:   # noqa: BLE001 -- the permanent half of the headline must still be printed
         sampling = {"metric": "gcc_samples_per_s_n24_m48", "error": repr(e)}
 
+    # every N: BASELINE configs 2 and 5 (SCALE records them next to the headline)
+    try:
+        c2 = c2_leg(world, rank, local_rank, fp64_peak)
+    except Exception as e:   # noqa: BLE001
+        c2 = {"error": repr(e)}
+    try:
+        c5 = c5_legs(world, rank, local_rank, fp64_peak)
+    except Exception as e:   # noqa: BLE001
+        c5 = {"error": repr(e)}
+
     if rank == 0:
         # correctness gate on the timed result: long-double fixture of the same workload
         with open(os.path.join(REPO, "tests", "golden", "large_permanents.json")) as f:
@@ -592,10 +732,13 @@ def run_native(args):
             "result": {"re": result.real, "im": result.imag, "rel_err_vs_long_double_fixture": rel},
             "wall_s_timed_region": wall1 - wall0,
             "gcc_sampling": sampling,
+            "c2_batched_n20_m40": c2,
+            "c5_lossy_n30_m60": c5,
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["reference_python"] = reference_python_fixture()
+            line["cpu_baseline"]["reference_python_live"] = reference_python_live()
         if extra is not None:
             line["extra"] = extra
         print(json.dumps(line))

@@ -113,7 +113,42 @@ def c5_run(args):
     return time.perf_counter() - t0
 
 
+def bounded():
+    """--bounded: the ~25 s slice bench.py runs LIVE on the bench host (reference from baseline/_ref, THEBOSS_REFERENCE):
+    Glynn at N = 14 / 16 / 18 on one core, N = 16 over all cores, BASELINE config 1 as is, one small GCC-B run."""
+    cores = os.cpu_count()
+    flops = lambda n: (8 * n - 4) * 2.0 ** (n - 1)   # noqa: E731
+    out = {"reference": REF, "host": {"cpu": platform.processor() or platform.machine(), "cores": cores,
+                                      "python": platform.python_version(), "numpy": np.__version__}}
+    c4 = {}
+    for n in (14, 16, 18):
+        dt, _ = c4_one(n)
+        c4[str(n)] = {"seconds": dt, "permanents_per_s": 1.0 / dt, "ns_per_term": dt / 2 ** (n - 1) * 1e9}
+    sec30 = c4["18"]["seconds"] * flops(30) / flops(18)
+    out["glynn_1core"] = c4
+    out["glynn_n30_permanents_per_s_1core_extrapolated"] = 1.0 / sec30
+    dt, cnt = c1_run(1000)
+    out["c1_gcc_n5_m10_1core"] = {"samples": cnt, "seconds": dt, "samples_per_s": cnt / dt}
+    dt = gccb_run((10, 4, 11))
+    out["gccb_n10_m20_1core"] = {"samples": 4, "seconds": dt, "samples_per_s": 4 / dt,
+                                 "n24_samples_per_s_extrapolated": 4 / dt * (2.0 ** 10 * 10) / (2.0 ** 24 * 24)}
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(c3_one, [4] * cores)   # warm the workers (imports)
+        t0 = time.perf_counter()
+        pool.map(c4_one, [16] * (2 * cores))
+        dt = time.perf_counter() - t0
+    rate = 2 * cores / dt
+    out["glynn_all_cores"] = {"n": 16, "permanents": 2 * cores, "cores": cores, "seconds": dt, "permanents_per_s": rate,
+                              "n30_permanents_per_s_extrapolated": rate * flops(16) / flops(30)}
+    out["note"] = ("unmodified Python reference (theboss v3.0.1 from baseline/_ref + the guancodes stand-in of oracle/refshim) timed on THIS "
+                   "host; n = 30 / n = 24 figures are EXTRAPOLATED by (8N-4) 2^(N-1) resp. 2^n n and say so in their key")
+    json.dump(out, sys.stdout)
+    print()
+
+
 def main():
+    if "--bounded" in sys.argv:
+        return bounded()
     quick = "--quick" in sys.argv
     cores = os.cpu_count()
     out = {
