@@ -47,7 +47,9 @@ typedef enum {
                                  (bs_permanent_calculator_base.py:61-72, :179-180) */
     BP_ERR_UNSUPPORTED = -3,  /* size beyond BP_MAX_N / BP_MAX_MODES */
     BP_ERR_CUDA = -4,         /* CUDA runtime failure, see bp_last_error */
-    BP_ERR_NOMEM = -5
+    BP_ERR_NOMEM = -5,
+    BP_ERR_DOMAIN = -6        /* a step's probabilities do not sum to a positive finite number (e.g. an all-zero column of U):
+                               * numpy.random.choice raises ValueError in the reference's _sample_from_pmf; so does the binding */
 } bp_status;
 
 /* formula selector of the multiplicity / minors entry points.  All three name the same

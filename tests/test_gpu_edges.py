@@ -135,3 +135,47 @@ def test_sharded_sampling_equals_single_call(handle):
         lo, hi = shard_bounds(101, 4, r)
         parts.append(handle.gccb_simulate(U, s, hi - lo, seed=77, first_sample=lo))
     assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_a_step_without_a_distribution_raises_like_numpy_random_choice(handle):
+    """An all-zero input column of U leaves every output with probability 0: the reference's numpy.random.choice raises
+    ValueError ("probabilities do not sum to 1", generalized_cliffords_b_simulation_strategy.py:107-110); the device loop must not
+    place the particle in mode 0 instead (BP_ERR_DOMAIN -> ValueError)."""
+    U = workloads.haar(6, 6)
+    U[:, 1] = 0.0
+    s = np.array([1, 1, 1, 0, 0, 0], dtype=np.int32)
+    with pytest.raises(ValueError):
+        handle.gccb_simulate(U, s, 16, seed=3)
+    with pytest.raises(ValueError):
+        handle.gccb_pmf(U, np.array([0, 1, 0, 0, 0, 0], dtype=np.int32), np.zeros(6, dtype=np.int32))
+    ok = handle.gccb_simulate(workloads.haar(6, 6), s, 16, seed=3)            # the handle stays usable
+    assert np.all(ok.sum(axis=1) == 3)
+
+
+def test_concurrent_calculators_on_the_shared_default_handle(handle):
+    """Independent calculator objects in different Python threads share the process-wide handle of a device; its calls are
+    serialised by the binding (the C handle holds one staging buffer and one set of scratch slots)."""
+    import threading
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.chin_huh_permanent_calculator import ChinHuhPermanentCalculator
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.glynn_gray_permanent_calculator import GlynnGrayPermanentCalculator
+    rng = np.random.RandomState(5)
+    jobs = []
+    for i in range(4):
+        m = 6 + i
+        U = workloads.haar(m, 40 + i)
+        s = np.zeros(m, dtype=int); t = np.zeros(m, dtype=int)
+        for j in rng.randint(0, m, 5): s[j] += 1
+        for j in rng.randint(0, m, 5): t[j] += 1
+        cls = ChinHuhPermanentCalculator if i % 2 else GlynnGrayPermanentCalculator
+        jobs.append(cls(U, list(s), list(t)))
+    want = [c.compute_permanent() for c in jobs]
+    got = [[] for _ in jobs]
+
+    def run(i):
+        for _ in range(25):
+            got[i].append(jobs[i].compute_permanent())
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(len(jobs)):
+        assert all(v == want[i] for v in got[i]), i

@@ -20,7 +20,7 @@ BP_MAX_N = 40
 BP_MAX_MODES = 256
 FORMULA_RYSER, FORMULA_CHIN_HUH, FORMULA_GLYNN = 0, 1, 2
 
-BP_OK, BP_ERR_INVALID, BP_ERR_SHAPE, BP_ERR_UNSUPPORTED, BP_ERR_CUDA, BP_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+BP_OK, BP_ERR_INVALID, BP_ERR_SHAPE, BP_ERR_UNSUPPORTED, BP_ERR_CUDA, BP_ERR_NOMEM, BP_ERR_DOMAIN = 0, -1, -2, -3, -4, -5, -6
 
 
 class BossPermError(RuntimeError):
@@ -140,6 +140,8 @@ class Handle:
             msg = self._lib.bp_last_error(self._h).decode()
         if rc == BP_ERR_SHAPE:
             raise AttributeError(msg)   # bs_permanent_calculator_base.py:179-180
+        if rc == BP_ERR_DOMAIN:
+            raise ValueError(msg)       # numpy.random.choice: "probabilities do not sum to 1" (generalized_cliffords_b_simulation_strategy.py:107-110)
         raise BossPermError(rc, msg)
 
     @staticmethod

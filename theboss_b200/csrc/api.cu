@@ -13,7 +13,7 @@ int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int
                                int N, double *dA);
 int bp_fp64_peak_launch(bp_context *h, int iters, double *d_sink);
 int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
-                 long long B, double *d_out);
+                 long long B, double *d_out, const unsigned char *hS, const unsigned char *hT);
 
 static char g_global_err[512] = "no error";
 
@@ -75,7 +75,8 @@ static int bp_create_impl(int device, void *stream, bool own, bp_handle *out) {
     if (!h) return bp_fail(nullptr, BP_ERR_NOMEM, "bp_create: out of host memory");
     h->device = device;
     cudaDeviceProp prop;
-    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    bp_device_guard guard(device);
+    if ((e = guard.err) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
         delete h;
         return bp_fail(nullptr, BP_ERR_CUDA, "bp_create: %s", cudaGetErrorString(e));
     }
@@ -113,7 +114,7 @@ int bp_create_on_stream(int device, void *cuda_stream, bp_handle *out) { return 
 
 int bp_destroy(bp_handle h) {
     if (!h) return BP_OK;
-    cudaSetDevice(h->device);
+    bp_device_guard guard(h->device);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < 8; ++i)
         if (h->d_buf[i]) cudaFree(h->d_buf[i]);
@@ -128,7 +129,7 @@ int bp_destroy(bp_handle h) {
 
 int bp_synchronize(bp_handle h) {
     if (!h) return bp_fail(nullptr, BP_ERR_INVALID, "NULL handle");
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     BP_CUDA(h, cudaStreamSynchronize(h->stream));
     return BP_OK;
 }
@@ -146,14 +147,14 @@ int64_t bp_launch_count(bp_handle h) { return h ? h->launches : 0; }
 
 int bp_timer_start(bp_handle h) {
     if (!h) return bp_fail(nullptr, BP_ERR_INVALID, "NULL handle");
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     BP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     return BP_OK;
 }
 
 int bp_timer_stop(bp_handle h, float *elapsed_ms) {
     if (!h || !elapsed_ms) return bp_fail(h, BP_ERR_INVALID, "bp_timer_stop: NULL argument");
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     BP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     BP_CUDA(h, cudaEventSynchronize(h->ev1));
     BP_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
@@ -162,7 +163,7 @@ int bp_timer_stop(bp_handle h, float *elapsed_ms) {
 
 int bp_fp64_peak(bp_handle h, double target_ms, double *tflops) {
     if (!h || !tflops) return bp_fail(h, BP_ERR_INVALID, "bp_fp64_peak: NULL argument");
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     int rc = bp_reserve(h, BP_SLOT_MISC, sizeof(double) * 1024);
     if (rc) return rc;
     double *sink = (double *)h->d_buf[BP_SLOT_MISC];
@@ -191,7 +192,7 @@ int bp_fp64_peak(bp_handle h, double target_ms, double *tflops) {
 
 // ---- K1 --------------------------------------------------------------------------------------
 static int glynn_range_host(bp_handle h, const double *A, int N, uint64_t lo, uint64_t hi, double out_dd[4]) {
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     const size_t bytes = sizeof(double) * 2 * (size_t)N * N;
     int rc = bp_reserve(h, BP_SLOT_MATRIX, bytes);
     if (rc) return rc;
@@ -216,7 +217,7 @@ int bp_glynn_matrix_range(bp_handle h, const double *A, int N, uint64_t step_lo,
 
 int bp_glynn_matrix_range_dev(bp_handle h, const double *dA, int N, uint64_t step_lo, uint64_t step_hi, double *d_out_dd) {
     if (!h || !dA || !d_out_dd) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_dev: NULL argument");
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     return bp_k1_launch(h, dA, N, step_lo, step_hi, d_out_dd);
 }
 
@@ -247,7 +248,7 @@ int bp_glynn_single(bp_handle h, const double *U, int m, const int32_t *s, const
     if (ns != nt) return bp_fail(h, BP_ERR_SHAPE, "bp_glynn_single: %ld input vs %ld output particles", ns, nt);
     if (ns > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_glynn_single: n=%ld > %d", ns, BP_MAX_N);
     const int N = (int)ns;
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     const size_t ub = sizeof(double) * 2 * (size_t)m * m, sb = sizeof(int32_t) * (size_t)m;
     int rc;
     if ((rc = bp_reserve(h, BP_SLOT_AUX, ub))) return rc;
@@ -283,8 +284,8 @@ int bp_perm_batched_dev(bp_handle h, const double *dU, int m, const uint8_t *dS,
     if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched_dev: m=%d outside [1, %d]", m, BP_MAX_MODES);
     if (formula < BP_FORMULA_RYSER || formula > BP_FORMULA_GLYNN) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: formula %d", formula);
     if (B < 0) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: B=%lld", (long long)B);
-    BP_CUDA(h, cudaSetDevice(h->device));
-    return bp_k2_launch(h, dU, m, dS, dT, (long long)B, d_out);
+    BP_ON_DEVICE(h);
+    return bp_k2_launch(h, dU, m, dS, dT, (long long)B, d_out, nullptr, nullptr);
 }
 
 int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const uint8_t *T, int64_t B, int formula,
@@ -300,7 +301,7 @@ int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const
         if (ns != nt) return bp_fail(h, BP_ERR_SHAPE, "bp_perm_batched: item %lld has %ld input vs %ld output particles", (long long)b, ns, nt);
         if (ns > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: item %lld has n=%ld > %d", (long long)b, ns, BP_MAX_N);
     }
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     const size_t ub = sizeof(double) * 2 * (size_t)m * m, sb = (size_t)B * m, ob = sizeof(double) * 2 * (size_t)B;
     int rc;
     if ((rc = bp_reserve(h, BP_SLOT_AUX, ub))) return rc;
@@ -311,7 +312,7 @@ int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const
     unsigned char *dS = (unsigned char *)h->d_buf[BP_SLOT_STATE], *dT = dS + ((sb + 15) / 16) * 16;
     BP_CUDA(h, cudaMemcpyAsync(dS, S, sb, cudaMemcpyHostToDevice, h->stream));
     BP_CUDA(h, cudaMemcpyAsync(dT, T, sb, cudaMemcpyHostToDevice, h->stream));
-    rc = bp_k2_launch(h, (const double *)h->d_buf[BP_SLOT_AUX], m, dS, dT, (long long)B, (double *)h->d_buf[BP_SLOT_OUT]);
+    rc = bp_k2_launch(h, (const double *)h->d_buf[BP_SLOT_AUX], m, dS, dT, (long long)B, (double *)h->d_buf[BP_SLOT_OUT], S, T);
     if (rc) return rc;
     BP_CUDA(h, cudaMemcpyAsync(out, h->d_buf[BP_SLOT_OUT], ob, cudaMemcpyDeviceToHost, h->stream));
     BP_CUDA(h, cudaStreamSynchronize(h->stream));

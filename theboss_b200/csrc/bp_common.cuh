@@ -39,6 +39,28 @@ int bp_reserve_pinned(bp_context *h, size_t bytes);
                            cudaGetErrorString(_e), __FILE__, __LINE__);                      \
     } while (0)
 
+// Entry points make the handle's device current and restore the caller's device on return (a process that also uses
+// torch or a second handle must not find its current device switched behind its back).
+struct bp_device_guard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit bp_device_guard(int device) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != device) {
+            err = cudaSetDevice(device);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~bp_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+    bp_device_guard(const bp_device_guard &) = delete;
+    bp_device_guard &operator=(const bp_device_guard &) = delete;
+};
+#define BP_ON_DEVICE(h)                                                                      \
+    bp_device_guard _bp_guard((h)->device);                                                  \
+    if (_bp_guard.err != cudaSuccess)                                                        \
+        return bp_fail((h), BP_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (h)->device, cudaGetErrorString(_bp_guard.err))
+
 #define BP_CHECK_LAUNCH(h)                                                                   \
     do {                                                                                     \
         (h)->launches++;                                                                     \

@@ -44,16 +44,38 @@ __global__ void k2_prep_kernel(const unsigned char *__restrict__ S, const unsign
     atomicAdd(&bins[ns * 64 + (63 - bucket)], 1);   // descending cost inside each n
 }
 
-// exclusive scan of the 41*64 bins (one block) + per-n offsets
-__global__ void k2_scan_kernel(int *__restrict__ bins, int *__restrict__ n_offsets /*[42]*/) {
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int n = 0; n <= BP_MAX_N; ++n) {
-            n_offsets[n] = run;
-            for (int c = 0; c < 64; ++c) { const int v = bins[n * 64 + c]; bins[n * 64 + c] = run; run += v; }
-        }
-        n_offsets[BP_MAX_N + 1] = run;
+// exclusive scan of the 41*64 bins + per-n offsets: one block of 1024 threads, three bins per thread, warp-shuffle scans
+#define K2_NBINS ((BP_MAX_N + 1) * 64)
+__global__ void __launch_bounds__(1024) k2_scan_kernel(int *__restrict__ bins, int *__restrict__ n_offsets /*[42]*/) {
+    constexpr int PER = (K2_NBINS + 1023) / 1024;
+    __shared__ int warp_sum[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int v[PER], mine = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { const int i = t * PER + q; v[q] = i < K2_NBINS ? bins[i] : 0; mine += v[q]; }
+    int x = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+        warp_sum[lane] = w;
     }
+    __syncthreads();
+    int run = x - mine + (warp ? warp_sum[warp - 1] : 0);   // exclusive prefix of this thread's first bin
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = t * PER + q;
+        if (i < K2_NBINS) {
+            bins[i] = run;
+            if ((i & 63) == 0) n_offsets[i >> 6] = run;
+        }
+        run += v[q];
+    }
+    if (t == 1023) n_offsets[BP_MAX_N + 1] = run;
 }
 
 __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, int *__restrict__ bins,
@@ -75,80 +97,63 @@ __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, 
 // main kernel
 // ---------------------------------------------------------------------------------------------
 #define K2_PMAX 512
-struct __align__(16) K2Step { double blow; int off; int pad; };   // binomial product at the position; row byte offset | went-up bit
+struct __align__(16) K2Step { double blow; int off; int pad; };   // binomial product at the position; byte offset of the signed row that leads there
 
-// 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset
-// (PIN: volatile, so that loads of a loop-invariant row stay inside the term loop instead of occupying registers)
-template <int OFF, bool PIN>
+// 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset (one address register per row)
+template <int OFF>
 __device__ __forceinline__ double2 k2_lds(unsigned addr) {
     double2 v;
-    if (PIN) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
-    else     asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
     return v;
 }
-// sums[j] += sg * X2row[j], j = 0 .. N-1 (row given by its shared-window address: one register + immediates)
-template <int N, bool PIN, int J = 0>
-__device__ __forceinline__ void k2_row_update(unsigned row, double sg, double (&sr)[N], double (&si)[N]) {
+// sums[j] += row[j], j = 0 .. N-1
+template <int N, int J = 0>
+__device__ __forceinline__ void k2_row_add(unsigned row, double (&sr)[N], double (&si)[N]) {
     if constexpr (J < N) {
-        const double2 a = k2_lds<J * (int)sizeof(double2), PIN>(row);
-        sr[J] = fma(sg, a.x, sr[J]);
-        si[J] = fma(sg, a.y, si[J]);
-        k2_row_update<N, PIN, J + 1>(row, sg, sr, si);
+        const double2 a = k2_lds<J * (int)sizeof(double2)>(row);
+        sr[J] += a.x;
+        si[J] += a.y;
+        k2_row_add<N, J + 1>(row, sr, si);
     }
 }
-#ifndef K2_REGROW_MAX_N
-#define K2_REGROW_MAX_N 12   // up to this N the row of the inner digit is kept in registers (4N extra registers); measured at N=20: 3 warps/SMSP with LDS rows beat 2 warps with register rows (11.8 vs 12.3 ms on config 2)
-#endif
 
 template <int N>
 struct K2Cfg {
-    static constexpr bool REGROW = (N <= K2_REGROW_MAX_N);
-#ifndef K2_MINB_MID
-#define K2_MINB_MID 3
-#endif
-#ifndef K2_NCH_MID
-#define K2_NCH_MID 1
-#endif
-    static constexpr int MINB = (N <= 8) ? 4 : (N <= 20) ? K2_MINB_MID : (N <= 26) ? 3 : 2;
+    static constexpr int MINB = (N <= 8) ? 4 : (N <= 26) ? 3 : 2;
 };
-
-template <int N>
-__device__ __forceinline__ void k2_product(const double (&sr)[N], const double (&si)[N], double &pr, double &pi) {
-    constexpr int NCH = (N > 20) ? 4 : (N > K2_REGROW_MAX_N) ? K2_NCH_MID : (N >= 4 ? 2 : 1);   // fewer chains where the inner row occupies registers
-    cplx p[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { p[c].re = sr[c]; p[c].im = si[c]; }
-#pragma unroll
-    for (int j = NCH; j < N; ++j) {
-        cplx s = {sr[j], si[j]};
-        p[j % NCH] = cmul(p[j % NCH], s);
-    }
-#pragma unroll
-    for (int stride = 1; stride < NCH; stride <<= 1)
-#pragma unroll
-        for (int c = 0; c + stride < NCH; c += 2 * stride) p[c] = cmul(p[c], p[c + stride]);
-    pr = p[0].re; pi = p[0].im;
+__host__ __device__ inline size_t k2_smem_bytes(int N) {
+    return (size_t)(2 * N + 1) * N * sizeof(double2) + (size_t)N * GW_THREADS + 16;
 }
 
+// Product of the N column sums as a balanced tree, evaluated depth-first (at most log2 N partial products are live).
+// The columns of one mode are adjacent (the product side is expanded in mode order), so a mode that holds w particles
+// contributes its factor through ~log2 w squarings -- the rounding behaviour of the reference's `pow`
+// (bs_permanent_calculator_base.py:200-209) instead of w - 1 sequential multiplications.
+template <int N, int LO, int HI>
+__device__ __forceinline__ cplx k2_tree(const double (&sr)[N], const double (&si)[N]) {
+    if constexpr (HI - LO == 1) { cplx v = {sr[LO], si[LO]}; return v; }
+    else {
+        constexpr int MID = (LO + HI) / 2;
+        return cmul(k2_tree<N, LO, MID>(sr, si), k2_tree<N, MID, HI>(sr, si));
+    }
+}
 
-// The walk of one item is organised like the minors kernel's (minors_kernel.cu): rows of L0 + 1 terms that
-// differ only in the inner digit 0 (largest multiplicity; swept up on even rows, down on odd ones), rows
-// indexed by the sub-walk over digits 1 .. D-1; the low digits of that sub-walk follow a per-block table
-// (period P), the generic Guan stepper only carries into the digits above it.  Threads own whole periods.
+// The walk of one item is organised like the minors kernel's (minors_kernel.cu): ONE uniform term loop.  The lowest digits
+// (digit 0 = the largest multiplicity first) follow a per-block step table of period P; inside a period every term fetches
+// the 16-byte entry of the next position, multiplies the N column sums, accumulates, and ADDS the signed row of the digit that
+// changes (shared-memory image: +2X rows, -2X rows, a zero row for the sentinel steps at both table ends).  The generic Guan
+// stepper only carries into the digits above the table, once per period.  Threads own whole periods.
 template <int N>
 __global__ void __launch_bounds__(GW_THREADS, K2Cfg<N>::MINB)
 k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restrict__ S,
                const unsigned char *__restrict__ T, const K2Meta *__restrict__ meta,
-               const int *__restrict__ order, int first, double *__restrict__ partials) {
-    constexpr bool REGROW = K2Cfg<N>::REGROW;
+               const int *__restrict__ order, int first, double *__restrict__ partials, double *__restrict__ out) {
+    constexpr int ROWBYTES = N * (int)sizeof(double2);
+    extern __shared__ __align__(16) unsigned char k2_smem[];
     __shared__ GuanItem item;
     __shared__ short col_mode[N];
-    __shared__ double2 X2[N * N];                       // 2 * X[v][j], D <= N rows
-    __shared__ unsigned char rdig[N * GW_THREADS];      // per-thread digit vectors (column = thread)
     __shared__ double red[4 * (GW_THREADS / 32)];
-    __shared__ double bin0[BP_MAX_N + 2];
-    // step tables of the low digits, indexed by the DESTINATION position inside a period (see minors_kernel.cu)
-    __shared__ K2Step fwd[K2_PMAX], bwd[K2_PMAX];
+    __shared__ K2Step fwd[K2_PMAX + 2], bwd[K2_PMAX + 2];   // indexed by destination position + 1; entries 0 and P + 1: sentinels
     __shared__ int low_digits;
     __shared__ unsigned period;
 
@@ -158,14 +163,15 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     const unsigned char *prod = (me.walk_outputs ? S : T) + (long long)b * m;
     if (threadIdx.x == 0) {
         guan_item_build(item, walk, m, /*inner_first=*/true);
+    } else if (threadIdx.x == 32) {
         int c = 0;
         for (int v = 0; v < m; ++v)
             for (int a = 0; a < prod[v] && c < N; ++a) col_mode[c++] = (short)v;
-        for (int r = 0; r <= (int)item.lim[0]; ++r)
-            bin0[r] = gw_binom(item.mult[0], r) * (item.D == 1 ? gw_top_weight(item, r) : 1.0);
     }
     __syncthreads();
     const int D = item.D;
+    double2 *X2 = reinterpret_cast<double2 *>(k2_smem);             // rows [0, D): +2X, [D, 2D): -2X, row 2D: 0
+    unsigned char *rdig = k2_smem + (size_t)(2 * N + 1) * N * sizeof(double2);   // per-thread digit vectors (column = thread)
     const double2 *U2 = reinterpret_cast<const double2 *>(U);
     for (int e = threadIdx.x; e < D * N; e += GW_THREADS) {
         const int v = e / N, j = e - v * N;
@@ -173,16 +179,17 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
         // U[out_mode][in_mode]: walking outputs -> rows of U, walking inputs -> columns of U
         const double2 u = me.walk_outputs ? U2[wm * m + pm] : U2[pm * m + wm];
         X2[e] = make_double2(2.0 * u.x, 2.0 * u.y);
+        X2[D * N + e] = make_double2(-2.0 * u.x, -2.0 * u.y);
     }
-    const int L0 = item.lim[0];
-    const unsigned long long rows = item.terms / (unsigned long long)(L0 + 1);
+    for (int j = threadIdx.x; j < N; j += GW_THREADS) X2[2 * D * N + j] = make_double2(0.0, 0.0);
+    const unsigned long long terms = item.terms;
     const unsigned long long nthreads = (unsigned long long)gridDim.y * GW_THREADS;
     if (threadIdx.x == 0) {
-        unsigned long long raw = (rows + nthreads - 1) / nthreads, P = 1;
-        int a = 0;
-        for (int v = 1; v < D; ++v) {
+        unsigned long long raw = (terms + nthreads - 1) / nthreads, P = 1;
+        int a = -1;
+        for (int v = 0; v < D; ++v) {
             const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
-            if (nxt * 16 > raw || nxt > K2_PMAX) break;
+            if (v > 0 && (nxt * 16 > raw || nxt > K2_PMAX)) break;   // digit 0 always: work is dealt out in whole sweeps of it
             P = nxt; a = v;
         }
         period = (unsigned)P;
@@ -195,7 +202,7 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
         double bprod = 1.0;
         unsigned q = p, qm = p ? p - 1 : 0;
         int chg = 0, up = 0;
-        for (int v = 1; v <= a_low; ++v) {
+        for (int v = 0; v <= a_low; ++v) {
             const unsigned R = (unsigned)item.lim[v] + 1u;
             unsigned d = q % R; q /= R;
             unsigned dm = qm % R; qm /= R;
@@ -206,50 +213,48 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
             if (v == D - 1) c *= gw_top_weight(item, rv);
             bprod *= c;
         }
-        const int rowbytes = N * (int)sizeof(double2);
-        fwd[p].blow = bprod; fwd[p].off = chg * rowbytes | up; fwd[p].pad = 0;
-        bwd[p].blow = bprod;
-        if (p == P - 1) { bwd[p].off = 0; bwd[p].pad = 0; }
-        if (p) { bwd[p - 1].off = chg * rowbytes | (up ^ 1); bwd[p - 1].pad = 0; }
+        // a digit that goes UP lowers its coefficient w - 2 r by 2: the negated row
+        const int zero_row = 2 * D * ROWBYTES;
+        fwd[p + 1].blow = bprod; fwd[p + 1].off = p ? (chg + (up ? D : 0)) * ROWBYTES : zero_row; fwd[p + 1].pad = 0;
+        bwd[p + 1].blow = bprod;
+        if (p == P - 1) { bwd[p + 1].off = zero_row; bwd[p + 1].pad = 0; }
+        if (p) { bwd[p].off = (chg + (up ? 0 : D)) * ROWBYTES; bwd[p].pad = 0; }
+        if (p == 0) {
+            fwd[P + 1].blow = 0.0; fwd[P + 1].off = zero_row; fwd[P + 1].pad = 0;
+            bwd[0].blow = 0.0; bwd[0].off = zero_row; bwd[0].pad = 0;
+        }
     }
     __syncthreads();
 
     // whole periods are dealt out to the threads of all chunk blocks of this item
-    const unsigned long long nper = rows / P;
+    const unsigned long long nper = terms / P;
     const unsigned long long tidx = (unsigned long long)blockIdx.y * GW_THREADS + threadIdx.x;
     const unsigned long long pbase = nper / nthreads, prem = nper % nthreads;
-    const unsigned long long my_periods = pbase + (tidx < prem ? 1ull : 0ull);
-    const unsigned long long row_start = (tidx * pbase + (tidx < prem ? tidx : prem)) * P;
+    const unsigned my_periods = (unsigned)(pbase + (tidx < prem ? 1ull : 0ull));   // (<= 2^39 terms over >= 128 threads: fits 32 bits)
+    const unsigned long long hi0 = tidx * pbase + (tidx < prem ? tidx : prem);
     dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
 
     if (my_periods > 0) {
-        const unsigned my_rows = (unsigned)(my_periods * P);   // per-thread row counts fit 32 bits (<= 2^39 terms over >= 128 threads)
         unsigned char *r = rdig + threadIdx.x;
         GuanState st;
-        const unsigned long long hi0 = row_start / P;
         guan_seek(item, hi0, r, st, /*v0=*/a_low + 1);
         int pos = (hi0 & 1ull) ? (int)P - 1 : 0;
         int pdir = (hi0 & 1ull) ? -1 : 1;
-        unsigned off = 0;
-        int r0 = (row_start & 1ull) ? L0 : 0;
-        int dir0 = (row_start & 1ull) ? -1 : 1;
         double sr[N], si[N];
-        double x0r[REGROW ? N : 1], x0i[REGROW ? N : 1];
 #pragma unroll
         for (int j = 0; j < N; ++j) { sr[j] = 0.0; si[j] = 0.0; }
-        int par = r0;
+        int par = 0;
         {
             unsigned q = (unsigned)pos;
 #pragma unroll 1
             for (int v = 0; v < D; ++v) {
                 int rv;
-                if (v == 0) rv = r0;
-                else if (v <= a_low) {
+                if (v <= a_low) {
                     const unsigned R = (unsigned)item.lim[v] + 1u;
                     const unsigned d = q % R; q /= R;
                     rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
                 } else rv = (int)r[v * GW_THREADS];
-                if (v > 0) par += rv;
+                par += rv;
                 const double c = 0.5 * (double)((int)item.mult[v] - 2 * rv);
                 const double2 *row = X2 + v * N;
 #pragma unroll
@@ -260,83 +265,58 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
                 }
             }
         }
-        if (REGROW) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) { const double2 a = X2[j]; x0r[j] = a.x; x0i[j] = a.y; }
-        }
-        double sgn = (par & 1) ? -1.0 : 1.0;
-        double bout = st.binom * fwd[pos].blow;
+        double bsgn = (par & 1) ? -st.binom : st.binom;      // sign of the term x binomial product of the digits above the table
         const K2Step *tab = (pdir > 0) ? fwd : bwd;
-        // shared-window address of X2, kept opaque so that row loads use ONE address register plus immediates
+        double blow = fwd[pos + 1].blow;
+        // shared-window address of the image, kept opaque so that row loads use ONE address register plus immediates
         unsigned x2base = (unsigned)__cvta_generic_to_shared(X2);
         asm volatile("" : "+r"(x2base));
-        double w0 = bin0[r0];                                // weight of digit 0, fetched one term ahead
         double wr = 0.0, wi = 0.0;
         unsigned cnt = 0;
 
 #pragma unroll 1
-        for (unsigned q = 0;;) {
-            // ---- plan the step to the next row now, so that its table / digit loads overlap the sweep below
-            const bool have_next = q + 1 < my_rows;
-            int off_next = 0;
-            double bout_next = 0.0;
-            if (have_next) {
-                if (++off < P) {
-                    pos += pdir;
-                    const K2Step e = tab[pos];
-                    off_next = e.off;
-                    bout_next = st.binom * e.blow;
-                } else {
-                    int delta;
-                    const int v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
-                    off_next = v * (N * (int)sizeof(double2)) | (delta > 0 ? 1 : 0);
-                    off = 0;
-                    pdir = -pdir;
-                    tab = (pdir > 0) ? fwd : bwd;
-                    bout_next = st.binom * fwd[pos].blow;
-                }
-            }
-            // ---- inner sweep over digit 0
+        for (unsigned per = 0;;) {
 #pragma unroll 1
-            for (int step = 0;; ++step) {
-                const double w = sgn * bout * w0;
-                double pr, pi;
-                k2_product<N>(sr, si, pr, pi);
-                wr = fma(w, pr, wr);
-                wi = fma(w, pi, wi);
-                if (++cnt == 64u) {
+            for (unsigned i = 0; i < P; ++i) {
+                pos += pdir;
+                const K2Step e = tab[pos + 1];               // step to the NEXT position, fetched ahead of the product
+                const double w = bsgn * blow;
+                const cplx pr = k2_tree<N, 0, N>(sr, si);
+                wr = fma(w, pr.re, wr);
+                wi = fma(w, pr.im, wi);
+                if (++cnt == 64u) {                          // plain accumulation over 64 terms, double-double beyond
                     cnt = 0;
                     acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
                     wr = 0.0; wi = 0.0;
                 }
-                const bool last = (step == L0);
-                if (!last) r0 += dir0;
-                w0 = bin0[r0];
-                if (last) break;
-                sgn = -sgn;
-                const double sg = (dir0 > 0) ? -1.0 : 1.0;        // sums -= 2 * dir0 * X[0]
-                if (REGROW) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) { sr[j] = fma(sg, x0r[j], sr[j]); si[j] = fma(sg, x0i[j], si[j]); }
-                } else {
-                    k2_row_update<N, true>(x2base, sg, sr, si);
-                }
+                bsgn = -bsgn;
+                blow = e.blow;
+                k2_row_add<N>(x2base + (unsigned)e.off, sr, si);
             }
-            dir0 = -dir0;
-            // ---- next row
-            if (!have_next) break;
-            ++q;
-            sgn = -sgn;
-            bout = bout_next;
-            k2_row_update<N, false>(x2base + (unsigned)(off_next & ~1), (off_next & 1) ? -1.0 : 1.0, sr, si);   // sums -= 2 * delta * X[v]
+            // ---- period boundary: one Guan step of the digits above the table; the table digits stay and reverse
+            if (++per >= my_periods) break;
+            pos -= pdir;
+            pdir = -pdir;
+            tab = (pdir > 0) ? fwd : bwd;
+            blow = fwd[pos + 1].blow;
+            int delta;
+            const int v = guan_step(item, r, st, delta, /*v0=*/a_low + 1);
+            k2_row_add<N>(x2base + (unsigned)((v + (delta > 0 ? D : 0)) * ROWBYTES), sr, si);
+            bsgn = (bsgn < 0.0) ? -st.binom : st.binom;
         }
         acc_re = dd_add_d(acc_re, wr);
         acc_im = dd_add_d(acc_im, wi);
     }
     block_reduce_dd(acc_re, acc_im, red);
     if (threadIdx.x == 0) {
-        double *o = partials + 4 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
-        o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo;
+        if (gridDim.y == 1) {   // the whole walk of the item in this block: finish here, 2^-n (chin_huh_permanent_calculator.py:41)
+            const double scale = ldexp(1.0, -N);
+            out[2 * (size_t)b] = (acc_re.hi + acc_re.lo) * scale;
+            out[2 * (size_t)b + 1] = (acc_im.hi + acc_im.lo) * scale;
+        } else {
+            double *o = partials + 4 * ((size_t)blockIdx.x * gridDim.y + blockIdx.y);
+            o[0] = acc_re.hi; o[1] = acc_re.lo; o[2] = acc_im.hi; o[3] = acc_im.lo;
+        }
     }
 }
 
@@ -366,7 +346,7 @@ __global__ void k2_empty_kernel(const int *__restrict__ order, int first, int co
     out[2 * b] = 1.0; out[2 * b + 1] = 0.0;
 }
 
-typedef void (*k2_fn)(const double *, int, const unsigned char *, const unsigned char *, const K2Meta *, const int *, int, double *);
+typedef void (*k2_fn)(const double *, int, const unsigned char *, const unsigned char *, const K2Meta *, const int *, int, double *, double *);
 template <int N>
 static void k2_entry(k2_fn *fn) {
     fn[N] = k2_perm_kernel<N>;
@@ -374,37 +354,86 @@ static void k2_entry(k2_fn *fn) {
 }
 static k2_fn g_k2_fn[BP_MAX_N + 1];
 
-// All pointers are device pointers.  Enqueues prep + sort + one launch per distinct n; needs one
-// small D2H copy (per-n offsets) in the middle, so it synchronises the stream once.
+#include <algorithm>
+#include <vector>
+
+// Batches up to this size are prepared (particle numbers, walk side, cost order) on the host while the matrix uploads: no
+// prep / scan / scatter launches -- a lone compute_permanent() is one copy in, ONE kernel, one copy out.
+#define K2_HOST_PREP_MAX 256
+
+// dU, dS, dT, d_out are device pointers.  hS / hT: the same occupations in host memory, or NULL (device-pointer entry point).
+// With host occupations the per-n item counts are known without asking the device, so nothing synchronises the stream;
+// without them one small D2H copy (the per-n offsets) does.
 int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
-                 long long B, double *d_out) {
+                 long long B, double *d_out, const unsigned char *hS, const unsigned char *hT) {
     static const bool ready = [] { k2_entry<BP_MAX_N>(g_k2_fn); return true; }();   // thread-safe one-time registration
     (void)ready;
     if (B <= 0) return BP_OK;
     if (B > 0x7fffffffll) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: B=%lld items exceeds 2^31-1", B);
     const size_t meta_bytes = sizeof(K2Meta) * (size_t)B, order_bytes = sizeof(int) * (size_t)B;
-    const size_t bins_bytes = sizeof(int) * ((BP_MAX_N + 1) * 64 + BP_MAX_N + 2);
+    const size_t bins_bytes = sizeof(int) * (K2_NBINS + BP_MAX_N + 2);
     int rc = bp_reserve(h, BP_SLOT_ITEMS, meta_bytes + order_bytes + bins_bytes + 64);
     if (rc) return rc;
-    if ((rc = bp_reserve_pinned(h, 4096))) return rc;
     char *base = (char *)h->d_buf[BP_SLOT_ITEMS];
     K2Meta *meta = (K2Meta *)base;
     int *order = (int *)(base + ((meta_bytes + 15) / 16) * 16);
     int *bins = (int *)((char *)order + ((order_bytes + 15) / 16) * 16);
-    int *n_offsets = bins + (BP_MAX_N + 1) * 64;
-    BP_CUDA(h, cudaMemsetAsync(bins, 0, bins_bytes, h->stream));
-    const int tb = 256, gb = (int)((B + tb - 1) / tb);
-    k2_prep_kernel<<<gb, tb, 0, h->stream>>>(dS, dT, m, B, meta, bins);
-    BP_CHECK_LAUNCH(h);
-    k2_scan_kernel<<<1, 32, 0, h->stream>>>(bins, n_offsets);
-    BP_CHECK_LAUNCH(h);
-    k2_scatter_kernel<<<gb, tb, 0, h->stream>>>(meta, B, bins, order, d_out);
-    BP_CHECK_LAUNCH(h);
-    int *h_off = (int *)h->h_pin;
-    BP_CUDA(h, cudaMemcpyAsync(h_off, n_offsets, sizeof(int) * (BP_MAX_N + 2), cudaMemcpyDeviceToHost, h->stream));
-    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    int *n_offsets = bins + K2_NBINS;
     int off[BP_MAX_N + 2];
-    for (int i = 0; i < BP_MAX_N + 2; ++i) off[i] = h_off[i];
+    if (hS && hT && B <= K2_HOST_PREP_MAX) {
+        // ---- small batch: everything the prep kernels would compute, on the host
+        const size_t pin_need = ((meta_bytes + 15) / 16) * 16 + order_bytes + 64;
+        if ((rc = bp_reserve_pinned(h, pin_need + 4096))) return rc;
+        // (every entry point ends with a stream synchronisation: the staging buffer is never in flight here)
+        K2Meta *hm = (K2Meta *)h->h_pin;
+        int *ho = (int *)((char *)h->h_pin + ((meta_bytes + 15) / 16) * 16);
+        int counts[BP_MAX_N + 2] = {0};
+        for (long long b = 0; b < B; ++b) {
+            const unsigned char *s = hS + b * m, *t = hT + b * m;
+            int ns = 0;
+            for (int v = 0; v < m; ++v) ns += s[v];
+            const double cs = guan_terms_of(s, m), ct = guan_terms_of(t, m);
+            hm[b].n = ns;                                  // (sum(s) == sum(t) <= BP_MAX_N: checked by the caller)
+            hm[b].walk_outputs = (ct < cs) ? 1 : 0;
+            hm[b].log2cost = (float)log2(ct < cs ? ct : cs);
+            ho[b] = (int)b;
+            counts[ns]++;
+        }
+        std::stable_sort(ho, ho + B, [hm](int x, int y) {
+            return hm[x].n != hm[y].n ? hm[x].n < hm[y].n : hm[x].log2cost > hm[y].log2cost;   // by n, longest first inside
+        });
+        off[0] = 0;
+        for (int n = 0; n <= BP_MAX_N; ++n) off[n + 1] = off[n] + counts[n];
+        BP_CUDA(h, cudaMemcpyAsync(meta, hm, meta_bytes, cudaMemcpyHostToDevice, h->stream));
+        BP_CUDA(h, cudaMemcpyAsync(order, ho, order_bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        BP_CUDA(h, cudaMemsetAsync(bins, 0, bins_bytes, h->stream));
+        const int tb = 256, gb = (int)((B + tb - 1) / tb);
+        k2_prep_kernel<<<gb, tb, 0, h->stream>>>(dS, dT, m, B, meta, bins);
+        BP_CHECK_LAUNCH(h);
+        k2_scan_kernel<<<1, 1024, 0, h->stream>>>(bins, n_offsets);
+        BP_CHECK_LAUNCH(h);
+        k2_scatter_kernel<<<gb, tb, 0, h->stream>>>(meta, B, bins, order, d_out);
+        BP_CHECK_LAUNCH(h);
+        if (hS) {
+            // item counts per particle number from the host copy: no round trip to the device
+            int counts[BP_MAX_N + 2] = {0};
+            for (long long b = 0; b < B; ++b) {
+                int ns = 0;
+                const unsigned char *s = hS + b * m;
+                for (int v = 0; v < m; ++v) ns += s[v];
+                counts[ns]++;
+            }
+            off[0] = 0;
+            for (int n = 0; n <= BP_MAX_N; ++n) off[n + 1] = off[n] + counts[n];
+        } else {
+            if ((rc = bp_reserve_pinned(h, 4096))) return rc;
+            int *h_off = (int *)h->h_pin;
+            BP_CUDA(h, cudaMemcpyAsync(h_off, n_offsets, sizeof(int) * (BP_MAX_N + 2), cudaMemcpyDeviceToHost, h->stream));
+            BP_CUDA(h, cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < BP_MAX_N + 2; ++i) off[i] = h_off[i];
+        }
+    }
     for (int n = 0; n <= BP_MAX_N; ++n) {
         const int count = off[n + 1] - off[n];
         if (count <= 0) continue;
@@ -413,19 +442,32 @@ int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS
             BP_CHECK_LAUNCH(h);
             continue;
         }
-        // chunks per item: enough blocks to fill the GPU a few times over, but at least ~256 terms per thread
+        // chunk blocks per item: enough blocks to fill the GPU a few times over; ~512 terms per thread when the batch fills
+        // the GPU anyway (every block pays its setup), down to ~64 when a few items must spread over all SMs
+        const double worst = ldexp(1.0, n - 1);
         long long by_fill = ((long long)h->sm_count * 12 + count - 1) / count;
-        long long by_work = (long long)(ldexp(1.0, n - 1) / (GW_THREADS * 512.0));
+        const double per_thread = (count >= h->sm_count * 2) ? 512.0 : 64.0;
+        long long by_work = (long long)(worst / (GW_THREADS * per_thread));
         long long chunks = by_fill < by_work ? by_fill : by_work;
         if (chunks < 1) chunks = 1;
         if (chunks > 4096) chunks = 4096;
-        if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)count * (size_t)chunks))) return rc;
-        double *d_partials = (double *)h->d_buf[BP_SLOT_PARTIALS];
+        double *d_partials = nullptr;
+        if (chunks > 1) {
+            if ((rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)count * (size_t)chunks))) return rc;
+            d_partials = (double *)h->d_buf[BP_SLOT_PARTIALS];
+        }
+        const size_t smem = k2_smem_bytes(n);
+        if (smem > 20 * 1024) {   // static shared memory (step tables, item) takes ~18 KB of the 48 KB that need no opt-in
+            cudaError_t e = cudaFuncSetAttribute((const void *)g_k2_fn[n], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+        }
         dim3 grid((unsigned)count, (unsigned)chunks);
-        g_k2_fn[n]<<<grid, GW_THREADS, 0, h->stream>>>(dU, m, dS, dT, meta, order, off[n], d_partials);
+        g_k2_fn[n]<<<grid, GW_THREADS, smem, h->stream>>>(dU, m, dS, dT, meta, order, off[n], d_partials, d_out);
         BP_CHECK_LAUNCH(h);
-        k2_finish_kernel<<<(count + 127) / 128, 128, 0, h->stream>>>(order, off[n], count, (int)chunks, n, d_partials, d_out);
-        BP_CHECK_LAUNCH(h);
+        if (chunks > 1) {
+            k2_finish_kernel<<<(count + 127) / 128, 128, 0, h->stream>>>(order, off[n], count, (int)chunks, n, d_partials, d_out);
+            BP_CHECK_LAUNCH(h);
+        }
     }
     return BP_OK;
 }

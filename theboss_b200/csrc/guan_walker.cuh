@@ -145,7 +145,7 @@ __device__ inline void guan_item_build_warp(GuanItem &it, const unsigned char *o
 }
 
 // Term count of the halved walk without building the item (cost model of the scheduler).
-__device__ inline double guan_terms_of(const unsigned char *occ, int m) {
+__host__ __device__ inline double guan_terms_of(const unsigned char *occ, int m) {
     double full = 1.0;
     int best_w = 0;
     bool any = false;

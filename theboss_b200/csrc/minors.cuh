@@ -17,6 +17,9 @@ struct K3Finish {
     // launch slot -> sample (NULL: identity).  Runs whose samples stop after different numbers of steps launch only
     // the samples still active; partials are indexed by launch slot, every per-sample array by sample.
     const int *order;
+    // NULL or one int: bit 0 is set when a step's probabilities do not sum to a positive finite number (the reference's
+    // numpy.random.choice raises there; the entry points turn the flag into BP_ERR_DOMAIN after their final synchronisation)
+    int *err_flag;
 };
 
 int bp_k3_width(int k);

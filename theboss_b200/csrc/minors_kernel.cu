@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
         double total = 0.0;
         for (int j = 0; j < m; ++j) total += wgt[j];
         total_sh = total;
+        if (a.err_flag && !(total > 0.0 && total < 1.0 / 0.0)) atomicOr(a.err_flag, 1);   // zero, NaN or infinite: no distribution
     }
     __syncthreads();
     const double total = total_sh;

@@ -58,7 +58,7 @@ __global__ void k4_init_kernel(const unsigned char *__restrict__ s0_base, size_t
                                const double *__restrict__ tape, int tape_stride, long long samples,
                                unsigned char *__restrict__ occ_s, unsigned char *__restrict__ occ_t,
                                unsigned char *__restrict__ remaining, int *__restrict__ n_remaining,
-                               int *__restrict__ steps_total) {
+                               int *__restrict__ steps_total, int *__restrict__ err_flag) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= samples) return;
     const double *tp = tape + i * tape_stride;
@@ -76,7 +76,7 @@ __global__ void k4_init_kernel(const unsigned char *__restrict__ s0_base, size_t
             if (run > u) { found = true; break; }
             ++steps;
         }
-        if (!found) steps = n;   // rounding left the CDF below u: the reference would index past the end; clamp
+        if (!found) { steps = n; atomicOr(err_flag, 2); }   // the CDF never exceeds u (weights that do not sum to 1): the reference indexes past the end
     }
     steps_total[i] = steps;
     unsigned char *s = occ_s + i * m, *t = occ_t + i * m, *rem = remaining + i * (long long)n;
@@ -120,10 +120,10 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
                        double *pmf, const char *who) {
     if (!h || !U || !s || !t) return bp_fail(h, BP_ERR_INVALID, "%s: NULL argument", who);
     if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: m=%d outside [1, %d]", who, m, BP_MAX_MODES);
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     const size_t ub = sizeof(double) * 2 * (size_t)m * m;
     int rc;
-    if ((rc = bp_reserve_pinned(h, 2 * (size_t)m + 64 + sizeof(double) * 3 * (size_t)m))) return rc;
+    if ((rc = bp_reserve_pinned(h, 2 * (size_t)m + 64 + sizeof(double) * 3 * (size_t)m + 64))) return rc;
     unsigned char *hs = (unsigned char *)h->h_pin, *ht = hs + m;
     long k = 0, kt = 0;
     if ((rc = occ_to_u8(h, s, m, hs, &k, who))) return rc;
@@ -138,6 +138,8 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(double) * 3 * (size_t)m))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_MISC, 64))) return rc;
     unsigned long long *d_terms = (unsigned long long *)h->d_buf[BP_SLOT_MISC];
+    int *d_flag = (int *)(d_terms + 2);
+    BP_CUDA(h, cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
     BP_CUDA(h, cudaMemcpyAsync(h->d_buf[BP_SLOT_AUX], U, ub, cudaMemcpyHostToDevice, h->stream));
     unsigned char *d_s = (unsigned char *)h->d_buf[BP_SLOT_STATE], *d_t = d_s + m;
     BP_CUDA(h, cudaMemcpyAsync(d_s, hs, 2 * (size_t)m, cudaMemcpyHostToDevice, h->stream));
@@ -150,10 +152,14 @@ static int minors_host(bp_context *h, const double *U, int m, const int32_t *s, 
     a.U = dU; a.m = m; a.W = W; a.chunks = chunks; a.step = (int)k - 1; a.partials = d_part;
     a.terms = d_terms; a.per_block = bp_k3_per_block(h, (int)k, 1);
     a.occ_s = d_s; a.occ_t = d_t; a.minors_out = d_min; a.pmf_out = pmf ? d_pmf : nullptr;
+    a.err_flag = d_flag;
     if ((rc = bp_k3_finish_launch(h, a, 1))) return rc;
     double *hres = (double *)((char *)h->h_pin + ((2 * (size_t)m + 63) / 64) * 64);
+    int *h_flag = (int *)(hres + 3 * (size_t)m);
     BP_CUDA(h, cudaMemcpyAsync(hres, d_min, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+    BP_CUDA(h, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (pmf && *h_flag) return bp_fail(h, BP_ERR_DOMAIN, "%s: the probabilities of the step do not sum to a positive finite number", who);
     if (minors) memcpy(minors, hres, sizeof(double) * 2 * (size_t)m);
     if (pmf) memcpy(pmf, hres + 2 * (size_t)m, sizeof(double) * (size_t)m);
     return BP_OK;
@@ -195,7 +201,7 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
     if (n_samples < 0) return bp_fail(h, BP_ERR_INVALID, "%s: n_samples=%lld", who, (long long)n_samples);
     if (eta > 1.0) return bp_fail(h, BP_ERR_INVALID, "%s: eta=%g > 1", who, eta);
     if (n_samples == 0) return BP_OK;
-    BP_CUDA(h, cudaSetDevice(h->device));
+    BP_ON_DEVICE(h);
     const size_t n_states = per_sample ? (size_t)n_samples : 1;
     std::vector<unsigned char> s8(n_states * (size_t)m);
     int rc, n = 0;
@@ -240,12 +246,12 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
     // device) or when every sample has its own input state: such runs launch only the samples still active at step k
     // (launch slot -> sample through `order`, samples sorted by their step count, longest first).
     const bool ragged = per_sample || eta >= 0.0;
-    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 20) + u_count * (size_t)m + (size_t)m + 256;
+    const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 20) + u_count * (size_t)m + (size_t)m + 256 + 16;
     if ((rc = bp_reserve(h, BP_SLOT_AUX, ub * u_count + sizeof(double) * (size_t)(n + 2)))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_STATE, state_bytes))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_TAPE, sizeof(double) * (size_t)batch * stride))) return rc;
     if (!ragged && (rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)maxW * max_chunks * (size_t)batch))) return rc;
-    if (ragged && (rc = bp_reserve_pinned(h, sizeof(int) * 2 * (size_t)batch + 64))) return rc;
+    if ((rc = bp_reserve_pinned(h, (ragged ? sizeof(int) * 2 * (size_t)batch : 0) + 128))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_OUT, sizeof(int) * (size_t)batch * m))) return rc;
 
     double *dU = (double *)h->d_buf[BP_SLOT_AUX];
@@ -258,7 +264,8 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
     int *d_nrem = (int *)(d_terms + batch);
     int *d_steps = d_nrem + batch;
     int *d_order = d_steps + batch;
-    unsigned char *d_occ_s = (unsigned char *)(d_order + batch);
+    int *d_flag = d_order + batch;                       // bit 0: a step without a distribution, bit 1: particle-number draw out of range
+    unsigned char *d_occ_s = (unsigned char *)(d_flag + 4);
     unsigned char *d_occ_t = d_occ_s + (size_t)batch * m;
     unsigned char *d_rem = d_occ_t + (size_t)batch * m;
     unsigned char *d_s0 = d_rem + (size_t)batch * n;
@@ -268,8 +275,10 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
     std::vector<long long> active(n + 2, 0);   // active[k] = samples that take at least k steps
     const size_t u_stride = per_sample ? 2 * (size_t)m * m : 0, s0_stride = per_sample ? (size_t)m : 0;
 
+    int *h_flag = (int *)((char *)h->h_pin + (ragged ? sizeof(int) * 2 * (size_t)batch : 0) + 64);
     for (long long done = 0; done < n_samples; done += batch) {
         const long long S = (n_samples - done < batch) ? (n_samples - done) : batch;
+        BP_CUDA(h, cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
         if (per_sample) {
             BP_CUDA(h, cudaMemcpyAsync(dU, U + (size_t)done * 2 * m * m, ub * (size_t)S, cudaMemcpyHostToDevice, h->stream));
             BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data() + (size_t)done * m, (size_t)S * m, cudaMemcpyHostToDevice, h->stream));
@@ -283,7 +292,7 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
             BP_CHECK_LAUNCH(h);
         }
         k4_init_kernel<<<(unsigned)((S + 127) / 128), 128, 0, h->stream>>>(d_s0, s0_stride, m, n, eta >= 0.0 ? d_w : nullptr, d_tape, stride, S,
-                                                                          d_occ_s, d_occ_t, d_rem, d_nrem, d_steps);
+                                                                          d_occ_s, d_occ_t, d_rem, d_nrem, d_steps, d_flag);
         BP_CHECK_LAUNCH(h);
         for (int k = 0; k <= n + 1; ++k) active[k] = (k <= n) ? S : 0;
         if (ragged) {
@@ -325,13 +334,18 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
             a.tape = d_tape; a.tape_stride = stride; a.remaining = d_rem; a.n_remaining = d_nrem; a.n = n;
             a.steps_total = d_steps;
             a.order = ragged ? d_order : nullptr;
+            a.err_flag = d_flag;
             if ((rc = bp_k3_finish_launch(h, a, A))) return rc;
         }
         const long long cnt = S * m;
         k4_output_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(d_occ_t, cnt, d_out);
         BP_CHECK_LAUNCH(h);
         BP_CUDA(h, cudaMemcpyAsync(out + (size_t)done * m, d_out, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, h->stream));
+        BP_CUDA(h, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         BP_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (*h_flag & 1) return bp_fail(h, BP_ERR_DOMAIN, "%s: the probabilities of a sampling step do not sum to a positive finite number "
+                                        "(numpy.random.choice raises ValueError in the reference)", who);
+        if (*h_flag & 2) return bp_fail(h, BP_ERR_DOMAIN, "%s: the particle-number weights sum to less than a drawn uniform (eta = %g)", who, eta);
     }
     return BP_OK;
 }
