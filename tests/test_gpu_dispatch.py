@@ -59,3 +59,21 @@ def test_every_block_shape_gives_the_same_samples(tmp_path, default_run, env):
     assert np.abs(got["pmf"] - default_run["pmf"]).max() <= 1e-13
     scale = np.abs(default_run["minors"]).max()
     assert np.abs(got["minors"] - default_run["minors"]).max() <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("env", [
+    {"BP_K3_TREE_MAX_C": 6, "BP_K3_WARP_MAX_K": 0},   # two lanes from k = 7, FOUR lanes (k3_minors_kernel<4, C>) from k = 13
+    {"BP_K3_TREE_MAX_C": 8, "BP_K3_WARP_MAX_K": 6},   # two lanes from k = 9
+], ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
+def test_lane_split_variants_reproduce_the_seeded_reference_runs_through_the_strategies(env):
+    """The seeded runs of the UNMODIFIED reference (GCC-B, its uniform-loss variant and the lossy-network wrapper at n = 12 .. 16,
+    tests/golden/gccb_seeded_samples.npz) replayed through the drop-in strategy classes in a process whose dispatch knobs send the
+    steps k >= 13 to the four-lane kernels -- the layouts BASELINE config 5(ii) reaches at k >= 31, which no reference run can:
+    every sample must still equal the reference's bit for bit (lossy_networks_generalized_cliffords_simulation_strategy.py:53-83,
+    bs_cc_ryser_submatrices_permanent_calculator.py:80-119)."""
+    code = ("import os, sys; sys.path.insert(0, %r); from tests.test_host_logic import _check_seeded_gccb_fixture; "
+            "_check_seeded_gccb_fixture(os.path.join(%r, 'tests', 'golden')); print('seeded fixtures reproduced')" % (REPO, REPO))
+    e = {k: v for k, v in os.environ.items() if not k.startswith("BP_K3_")}
+    e.update({k: str(v) for k, v in env.items()})
+    run = subprocess.run([sys.executable, "-c", code], env=e, cwd=REPO, capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0 and "seeded fixtures reproduced" in run.stdout, run.stdout[-2000:] + run.stderr[-2000:]

@@ -144,7 +144,11 @@ def test_k30_minors_in_the_dilated_network_satisfy_the_laplace_expansion(handle,
     z = np.load(os.path.join(golden_dir, "minors_large.npz"))
     U, s, t = z["dilated_k30_U"], z["dilated_k30_s"], z["dilated_k30_t"]
     minors = handle.minors(U, s, t)
-    js = [0, 17, 59, 60, 101, 119]
+    # outcomes that CAN happen: any detector mode, and the loss modes of occupied inputs whose particle is not lost yet (a loss
+    # mode couples to exactly one input mode; every other placement has permanent 0 and no relative accuracy to speak of)
+    loss_modes = [60 + int(np.argmax(np.abs(U[60:, i]))) for i in np.nonzero(s)[0]]
+    js = [0, 17, 59] + [j for j in loss_modes if t[j] == 0][:3]
+    assert len(js) == 6
     S = np.repeat(s[None].astype(np.uint8), len(js), axis=0)
     T = np.repeat(t[None].astype(np.uint8), len(js), axis=0)
     T[np.arange(len(js)), js] += 1
