@@ -51,13 +51,15 @@ ISSUE_SLOTS = (6 * N_PHOTONS - 4) * 2.0 ** (N_PHOTONS - 1)    # FP64 instruction
 NOMINAL_FP64_TFLOPS = 37.0
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, exchange=None):
+    how = {"peer": "partials exchanged through peer memory (NVLink stores from the last block of K1, no NCCL launch)",
+           "nccl": "NCCL all-gather of 32 B partials"}.get(exchange, "all-gather of 32 B partials")
     return {
         "workload": "C4: single n=30 complex128 Gray-code Glynn permanent, Haar(60, seed 30) 30x30 submatrix, 2^29 Gray steps",
         "n": N_PHOTONS,
         "terms_per_step": 2 ** (N_PHOTONS - 1),
         "algorithmic_flops_per_step": ALG_FLOPS,
-        "sharding": f"Gray range split over {n_gpus} rank(s), all-gather of 32 B partials" if n_gpus > 1 else "single GPU",
+        "sharding": f"Gray range split over {n_gpus} rank(s), {how}" if n_gpus > 1 else "single GPU",
         "l2": "L2 flushed (256 MiB write) before every timed step; working set is 14.4 KB, path is FP64-compute-bound",
     }
 
@@ -713,7 +715,7 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, job.exchange),
             "clocks": clocks,
             "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": job.h2d_bytes,
                     "d2h_bytes_per_step": job.d2h_bytes},

@@ -37,6 +37,7 @@ extern "C" {
 #define BP_ABI_VERSION 1
 #define BP_MAX_N 40        /* largest explicit matrix / particle number of the register kernels */
 #define BP_MAX_MODES 256   /* largest interferometer dimension m */
+#define BP_MAX_PEERS 16     /* most ranks (GPUs of one node) of a peer-memory exchange */
 
 typedef struct bp_context *bp_handle;
 
@@ -98,6 +99,27 @@ int bp_glynn_matrix_range(bp_handle h, const double *A, int N, uint64_t step_lo,
                           double out_dd[4]);
 int bp_glynn_matrix_range_dev(bp_handle h, const double *dA, int N, uint64_t step_lo,
                               uint64_t step_hi, double *d_out_dd);
+
+/* Declares the device matrix dA RESIDENT: its contents stay as they are until the next bp_glynn_set_resident call on this
+ * handle (same pointer again = "the contents changed", NULL = no resident matrix).  Range calls on a resident matrix reuse the
+ * kernel's constant-bank image of it instead of copying it again at every launch (12 us per call).  No reference counterpart:
+ * the reference rebuilds its matrix view per call (glynn_gray_permanent_calculator.py:41-53). */
+int bp_glynn_set_resident(bp_handle h, const double *dA);
+
+/* ---- K1 sharded over the GPUs of one node: partial exchange over peer memory (NVLink) --------------------------------
+ * One process per GPU.  The reference has no distributed path; this is the exchange step of the sharded
+ * Glynn permanent of BASELINE.json configs[3]: every rank evaluates a slice of the Gray range and needs all ranks' 32-byte
+ * double-double partials.  bp_exchange_create allocates this rank's slot buffer and returns its CUDA IPC handle; the caller
+ * all-gathers the `world` handles (64 bytes each, rank order) by any means and passes them to bp_exchange_connect, which maps
+ * the peers' buffers.  bp_glynn_matrix_range_exchange then is bp_glynn_matrix_range_dev fused with the exchange: the LAST block
+ * of the kernel stores this rank's partial straight into every peer's slot buffer, waits for the `world` partials of this call
+ * to arrive in its own, and writes them in rank order to d_out_all[world][4].  Collective: every rank must make the same
+ * sequence of calls.  A peer that does not arrive within 10 s leaves NaNs in its row of d_out_all. */
+int bp_exchange_create(bp_handle h, int world, int rank, unsigned char ipc_handle_out[64]);
+int bp_exchange_connect(bp_handle h, const unsigned char *ipc_handles /* [world][64] */);
+int bp_exchange_destroy(bp_handle h);
+int bp_glynn_matrix_range_exchange(bp_handle h, const double *dA, int N, uint64_t step_lo, uint64_t step_hi,
+                                   double *d_out_all);
 
 /* Full calculator call: builds the effective scattering matrix of (U, s, t) on the device
  * (boson_sampling_utilities.py:595-626) and evaluates it.  s, t: length m occupations.

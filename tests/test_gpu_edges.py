@@ -42,9 +42,9 @@ def test_all_ones_matrix_is_n_factorial(handle):
 def test_heavy_bunching_up_to_forty_particles(handle, orc):
     """n = 40 (BP_MAX_N) concentrated in a few modes: tiny walks, large binomial weights.  With 20-fold
     bunching the Chin-Huh sum cancels ~10 digits in ANY float64 evaluation (the reference's included), so
-    the bar is 1e-10 or 100x the error of the double-precision restatement of the reference, whichever is
-    looser (the kernel multiplies the 40 expanded factors one by one, the reference uses pow(): ~4x more roundings
-    per term, amplified by the same cancellation)."""
+    the bar is 1e-10 or 12x the error of the double-precision restatement of the reference, whichever is
+    looser (measured, scripts/bunching_accuracy.py: kernel 8e-10 / 1e-9 / 1.5e-11 / 9e-11 against 9e-11 / 9e-10 / 1.3e-12 / 6e-11
+    of the reference's arithmetic; round 1, before the product tree: up to 2e-9)."""
     m = 8
     U = workloads.haar(m, 40)
     S = np.array([[20, 20, 0, 0, 0, 0, 0, 0], [40, 0, 0, 0, 0, 0, 0, 0], [10, 10, 10, 10, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 7, 33]], dtype=np.uint8)
@@ -53,7 +53,7 @@ def test_heavy_bunching_up_to_forty_particles(handle, orc):
     for b in range(len(S)):
         want = orc.guan_permanent(U, S[b], T[b], orc.CHIN_HUH, "ld")
         ref_err = abs(orc.guan_permanent(U, S[b], T[b], orc.CHIN_HUH, "d") - want) / abs(want)
-        assert abs(got[b] - want) <= max(1e-10, 100 * ref_err) * abs(want), (b, ref_err)
+        assert abs(got[b] - want) <= max(1e-10, 12 * ref_err) * abs(want), (b, ref_err)
 
 
 def test_max_mode_count(handle, orc):
@@ -82,7 +82,7 @@ def test_minors_with_41_input_particles(handle, orc):
     want = orc.submatrices(U, s, t, orc.CHIN_HUH, "ld")
     ref_err = np.abs(orc.submatrices(U, s, t, orc.CHIN_HUH, "d") - want).max() / np.abs(want).max()
     # 20-fold bunching: same float64 cancellation caveat as test_heavy_bunching_up_to_forty_particles
-    assert np.abs(got - want).max() <= max(1e-10, 100 * ref_err) * np.abs(want).max(), ref_err
+    assert np.abs(got - want).max() <= max(1e-10, 12 * ref_err) * np.abs(want).max(), ref_err
 
 
 def test_empty_and_degenerate_sampling_requests(handle):

@@ -49,6 +49,11 @@ SIGNATURES = {
     "bp_glynn_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp]),
     "bp_glynn_matrix_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, _dp]),
     "bp_glynn_matrix_range_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bp_glynn_set_resident": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bp_exchange_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bp_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bp_exchange_destroy": (C.c_int, [C.c_void_p]),
+    "bp_glynn_matrix_range_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "bp_glynn_single": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _dp]),
     "bp_perm_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "bp_perm_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
@@ -220,6 +225,28 @@ class Handle:
 
     def glynn_matrix_range_dev(self, dA_ptr: int, N: int, lo: int, hi: int, d_out_ptr: int):
         self._call("bp_glynn_matrix_range_dev", C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_ptr))
+
+    def glynn_set_resident(self, dA_ptr: Optional[int]):
+        """Declare a device matrix resident (None: no resident matrix); see include/bossperm.h."""
+        self._call("bp_glynn_set_resident", C.c_void_p(dA_ptr) if dA_ptr else None)
+
+    def exchange_create(self, world: int, rank: int) -> bytes:
+        """Allocate this rank's slot buffer of the peer-memory partial exchange; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_ubyte * 64)()
+        self._call("bp_exchange_create", int(world), int(rank), buf)
+        return bytes(buf)
+
+    def exchange_connect(self, ipc_handles) -> None:
+        """Map the peers' slot buffers: `ipc_handles` = the handles of all ranks in rank order (64 bytes each)."""
+        blob = b"".join(bytes(x) for x in ipc_handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._call("bp_exchange_connect", buf)
+
+    def exchange_destroy(self) -> None:
+        self._call("bp_exchange_destroy")
+
+    def glynn_matrix_range_exchange(self, dA_ptr: int, N: int, lo: int, hi: int, d_out_all_ptr: int):
+        self._call("bp_glynn_matrix_range_exchange", C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_all_ptr))
 
     def glynn_single(self, U: np.ndarray, s: np.ndarray, t: np.ndarray) -> complex:
         U, s, t = self._normalised(U, s, t)

@@ -8,7 +8,7 @@
 #include "bp_common.cuh"
 
 // kernels implemented in the other translation units
-int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_out_dd);
+int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_out_dd, double *d_exchange_out);
 int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int32_t *d_s, const int32_t *d_t,
                                int N, double *dA);
 int bp_fp64_peak_launch(bp_context *h, int iters, double *d_sink);
@@ -112,6 +112,8 @@ static int bp_create_impl(int device, void *stream, bool own, bp_handle *out) {
 int bp_create(int device, bp_handle *out) { return bp_create_impl(device, nullptr, true, out); }
 int bp_create_on_stream(int device, void *cuda_stream, bp_handle *out) { return bp_create_impl(device, cuda_stream, false, out); }
 
+static void exchange_release(bp_context *h);
+
 int bp_destroy(bp_handle h) {
     if (!h) return BP_OK;
     bp_device_guard guard(h->device);
@@ -120,6 +122,7 @@ int bp_destroy(bp_handle h) {
         if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->d_counter) cudaFree(h->d_counter);
+    exchange_release(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -200,7 +203,7 @@ static int glynn_range_host(bp_handle h, const double *A, int N, uint64_t lo, ui
     if ((rc = bp_reserve_pinned(h, bytes + 64))) return rc;
     memcpy(h->h_pin, A, bytes);
     BP_CUDA(h, cudaMemcpyAsync(h->d_buf[BP_SLOT_MATRIX], h->h_pin, bytes, cudaMemcpyHostToDevice, h->stream));
-    rc = bp_k1_launch(h, (const double *)h->d_buf[BP_SLOT_MATRIX], N, lo, hi, (double *)h->d_buf[BP_SLOT_OUT]);
+    rc = bp_k1_launch(h, (const double *)h->d_buf[BP_SLOT_MATRIX], N, lo, hi, (double *)h->d_buf[BP_SLOT_OUT], nullptr);
     if (rc) return rc;
     double *res = (double *)((char *)h->h_pin + ((bytes + 31) / 32) * 32);
     BP_CUDA(h, cudaMemcpyAsync(res, h->d_buf[BP_SLOT_OUT], sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -218,7 +221,83 @@ int bp_glynn_matrix_range(bp_handle h, const double *A, int N, uint64_t step_lo,
 int bp_glynn_matrix_range_dev(bp_handle h, const double *dA, int N, uint64_t step_lo, uint64_t step_hi, double *d_out_dd) {
     if (!h || !dA || !d_out_dd) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_dev: NULL argument");
     BP_ON_DEVICE(h);
-    return bp_k1_launch(h, dA, N, step_lo, step_hi, d_out_dd);
+    return bp_k1_launch(h, dA, N, step_lo, step_hi, d_out_dd, nullptr);
+}
+
+int bp_glynn_set_resident(bp_handle h, const double *dA) {
+    if (!h) return bp_fail(nullptr, BP_ERR_INVALID, "NULL handle");
+    h->resident_A = dA;
+    h->resident_gen++;      // same pointer again: new contents -> the constant-bank image is rebuilt once
+    return BP_OK;
+}
+
+// ---- K1 partial exchange over peer memory ----------------------------------------------------
+static void exchange_release(bp_context *h) {
+    for (int r = 0; r < BP_MAX_PEERS; ++r) {
+        if (h->xchg_mapped[r] && h->xchg_peer[r]) cudaIpcCloseMemHandle(h->xchg_peer[r]);
+        h->xchg_peer[r] = nullptr;
+        h->xchg_mapped[r] = false;
+    }
+    if (h->xchg_local) cudaFree(h->xchg_local);
+    h->xchg_local = nullptr;
+    h->xchg_world = 0; h->xchg_rank = 0; h->xchg_seq = 0;
+}
+
+int bp_exchange_create(bp_handle h, int world, int rank, unsigned char ipc_handle_out[64]) {
+    if (!h || !ipc_handle_out) return bp_fail(h, BP_ERR_INVALID, "bp_exchange_create: NULL argument");
+    if (world < 1 || world > BP_MAX_PEERS || rank < 0 || rank >= world)
+        return bp_fail(h, BP_ERR_INVALID, "bp_exchange_create: rank %d of %d (at most %d ranks)", rank, world, BP_MAX_PEERS);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    BP_ON_DEVICE(h);
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    exchange_release(h);
+    const size_t bytes = sizeof(double) * 8 * 2 * (size_t)world;      // two halves of `world` slots of 8 doubles
+    cudaError_t e = cudaMalloc((void **)&h->xchg_local, bytes);
+    if (e != cudaSuccess) return bp_fail(h, BP_ERR_NOMEM, "bp_exchange_create: cudaMalloc: %s", cudaGetErrorString(e));
+    BP_CUDA(h, cudaMemset(h->xchg_local, 0, bytes));                   // call numbers start at 1
+    cudaIpcMemHandle_t ipc;
+    if ((e = cudaIpcGetMemHandle(&ipc, h->xchg_local)) != cudaSuccess) {
+        exchange_release(h);
+        return bp_fail(h, BP_ERR_CUDA, "bp_exchange_create: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle_out, &ipc, 64);
+    h->xchg_world = world; h->xchg_rank = rank; h->xchg_seq = 0;
+    h->xchg_peer[rank] = h->xchg_local;
+    return BP_OK;
+}
+
+int bp_exchange_connect(bp_handle h, const unsigned char *ipc_handles) {
+    if (!h || !ipc_handles) return bp_fail(h, BP_ERR_INVALID, "bp_exchange_connect: NULL argument");
+    if (h->xchg_world < 1) return bp_fail(h, BP_ERR_INVALID, "bp_exchange_connect: bp_exchange_create comes first");
+    BP_ON_DEVICE(h);
+    for (int r = 0; r < h->xchg_world; ++r) {
+        if (r == h->xchg_rank || h->xchg_peer[r]) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, ipc_handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return bp_fail(h, BP_ERR_CUDA, "bp_exchange_connect: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        h->xchg_peer[r] = (double *)p;
+        h->xchg_mapped[r] = true;
+    }
+    return BP_OK;
+}
+
+int bp_exchange_destroy(bp_handle h) {
+    if (!h) return bp_fail(nullptr, BP_ERR_INVALID, "NULL handle");
+    BP_ON_DEVICE(h);
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    exchange_release(h);
+    return BP_OK;
+}
+
+int bp_glynn_matrix_range_exchange(bp_handle h, const double *dA, int N, uint64_t step_lo, uint64_t step_hi, double *d_out_all) {
+    if (!h || !dA || !d_out_all) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_exchange: NULL argument");
+    BP_ON_DEVICE(h);
+    return bp_k1_launch(h, dA, N, step_lo, step_hi, nullptr, d_out_all);
 }
 
 int bp_glynn_matrix(bp_handle h, const double *A, int N, double out[2]) {
@@ -265,7 +344,7 @@ int bp_glynn_single(bp_handle h, const double *U, int m, const int32_t *s, const
     const int32_t *d_s = (const int32_t *)h->d_buf[BP_SLOT_STATE];
     rc = bp_effective_matrix_launch(h, (const double *)h->d_buf[BP_SLOT_AUX], m, d_s, d_s + m, N, (double *)h->d_buf[BP_SLOT_MATRIX]);
     if (rc) return rc;
-    rc = bp_k1_launch(h, (const double *)h->d_buf[BP_SLOT_MATRIX], N, 0, 1ull << (N - 1), (double *)h->d_buf[BP_SLOT_OUT]);
+    rc = bp_k1_launch(h, (const double *)h->d_buf[BP_SLOT_MATRIX], N, 0, 1ull << (N - 1), (double *)h->d_buf[BP_SLOT_OUT], nullptr);
     if (rc) return rc;
     double *res = (double *)(pin + ((ub + 2 * sb + 31) / 32) * 32);
     BP_CUDA(h, cudaMemcpyAsync(res, h->d_buf[BP_SLOT_OUT], sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));

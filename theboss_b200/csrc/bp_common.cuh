@@ -24,6 +24,15 @@ struct bp_context {
     size_t h_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned int *d_counter = nullptr;   // K1: block arrival counter of the fused finish (always zero between launches)
+    // K1: device matrix declared resident (bp_glynn_set_resident): its constant-bank image is reused while it is the last one written
+    const double *resident_A = nullptr;
+    uint64_t resident_gen = 0;
+    // K1 partial exchange over peer memory (bp_exchange_*): my slot buffer, the peers' (IPC-mapped), call counter
+    double *xchg_local = nullptr;
+    double *xchg_peer[BP_MAX_PEERS] = {nullptr};
+    bool xchg_mapped[BP_MAX_PEERS] = {false};
+    int xchg_world = 0, xchg_rank = 0;
+    uint64_t xchg_seq = 0;
     char err[512] = {0};
 };
 

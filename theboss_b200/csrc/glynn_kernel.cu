@@ -63,8 +63,9 @@ __device__ __forceinline__ void k1_product(const double (&sr)[N], const double (
     pi = p[0].im;
 }
 
-// Sums `nblocks` double-double complex partials in block order and scales by 2^scale_log2 (exact).  One warp.
-__device__ __forceinline__ void k1_sum_partials(const double *partials, int nblocks, int scale_log2, double *out_dd) {
+// Sums `nblocks` double-double complex partials in block order and scales by 2^scale_log2 (exact).  One warp; the result is
+// returned in every lane and, when out_dd is given, written there by lane 0.
+__device__ __forceinline__ void k1_sum_partials(const double *partials, int nblocks, int scale_log2, double *out_dd, double (&res)[4]) {
     const int lane = threadIdx.x & 31;
     dd re = {0.0, 0.0}, im = {0.0, 0.0};
     for (int b = lane; b < nblocks; b += 32) {
@@ -77,17 +78,59 @@ __device__ __forceinline__ void k1_sum_partials(const double *partials, int nblo
         re = dd_add(re, dd_shfl_down(re, d));
         im = dd_add(im, dd_shfl_down(im, d));
     }
-    if (lane == 0) {
-        out_dd[0] = ldexp(re.hi, scale_log2); out_dd[1] = ldexp(re.lo, scale_log2);
-        out_dd[2] = ldexp(im.hi, scale_log2); out_dd[3] = ldexp(im.lo, scale_log2);
+    res[0] = ldexp(re.hi, scale_log2); res[1] = ldexp(re.lo, scale_log2);
+    res[2] = ldexp(im.hi, scale_log2); res[3] = ldexp(im.lo, scale_log2);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) res[q] = __shfl_sync(0xffffffffu, res[q], 0);
+    if (lane == 0 && out_dd) { out_dd[0] = res[0]; out_dd[1] = res[1]; out_dd[2] = res[2]; out_dd[3] = res[3]; }
+}
+
+// Partial exchange over peer memory (bp_glynn_matrix_range_exchange).  Slot buffers hold 2 x world slots of 8 doubles
+// {re_hi, re_lo, im_hi, im_lo, call number, -, -, -}; calls alternate between the two halves, so a rank that is one call ahead
+// never overwrites a slot a slower peer still has to read (it cannot be two ahead: its own wait needs the peer's arrival).
+struct K1Exchange {
+    double *peer[BP_MAX_PEERS];     // slot buffer of every rank as mapped into this process (peer[rank] = the local one)
+    double *out_all;                // [world][4] on this device
+    unsigned long long seq;         // call number, >= 1
+    int world, rank;                // world == 0: no exchange
+};
+#define K1X_SLOT 8
+#define K1X_TIMEOUT_NS 10000000000ull
+
+__device__ __forceinline__ unsigned long long k1_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One warp of the last block: lane r < world stores this rank's partial into rank r's buffer (payload, system-wide fence, call
+// number), then waits for rank r's partial of the same call in the local buffer and copies it out.
+__device__ __forceinline__ void k1_exchange(const K1Exchange &x, const double (&res)[4]) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= x.world) return;
+    const size_t half = (size_t)(x.seq & 1ull) * (size_t)x.world;
+    volatile double *dst = x.peer[lane] + (half + (size_t)x.rank) * K1X_SLOT;
+    dst[0] = res[0]; dst[1] = res[1]; dst[2] = res[2]; dst[3] = res[3];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(dst + 4) = x.seq;
+    volatile double *src = x.peer[x.rank] + (half + (size_t)lane) * K1X_SLOT;
+    volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(src + 4);
+    const unsigned long long t0 = k1_globaltimer();
+    bool arrived = true;
+    while (*flag != x.seq) {
+        if (k1_globaltimer() - t0 > K1X_TIMEOUT_NS) { arrived = false; break; }
     }
+    __threadfence_system();
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x.out_all[4 * lane + q] = arrived ? src[q] : nan;
 }
 
 // Block epilogue shared by both kernels: thread 0 holds the block's partial.  With a counter (one kernel covers the whole
 // range) the last block to arrive adds all partials in block order -- the same order and arithmetic as glynn_finish_kernel,
-// so the result does not depend on which block is last -- and resets the counter for the next launch.
+// so the result does not depend on which block is last -- resets the counter for the next launch, and runs the exchange.
 __device__ __forceinline__ void k1_block_epilogue(dd acc_re, dd acc_im, double *__restrict__ partials, unsigned int *counter,
-                                                  int scale_log2, double *__restrict__ out_dd) {
+                                                  int scale_log2, double *__restrict__ out_dd, const K1Exchange &x) {
     __shared__ int is_last;
     if (threadIdx.x == 0) {
         double *o = partials + 4 * (size_t)blockIdx.x;
@@ -103,15 +146,17 @@ __device__ __forceinline__ void k1_block_epilogue(dd acc_re, dd acc_im, double *
     __syncthreads();
     if (is_last && threadIdx.x < 32) {
         __threadfence();
-        k1_sum_partials(partials, (int)gridDim.x, scale_log2, out_dd);
+        double res[4];
+        k1_sum_partials(partials, (int)gridDim.x, scale_log2, out_dd, res);
         if (threadIdx.x == 0) *counter = 0u;
+        if (x.world > 0) k1_exchange(x, res);
     }
 }
 
 template <int N>
 __global__ void __launch_bounds__(K1_THREADS, K1Cfg<N>::MINB)
 glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
-                  double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd) {
+                  double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd, const K1Exchange x) {
     __shared__ double2 sA2[N * N];                    // A, row-major (the column sums are kept halved)
     __shared__ double red[4 * (K1_THREADS / 32)];
 
@@ -174,7 +219,7 @@ glynn_gray_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64
     }
 
     block_reduce_dd(acc_re, acc_im, red);
-    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd);
+    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd, x);
 }
 
 
@@ -231,7 +276,7 @@ __device__ __forceinline__ void k1b_flip_const(double (&sr)[N], double (&si)[N],
 template <int N>
 __global__ void __launch_bounds__(K1BCfg<N>::THREADS, 1)
 glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
-                    double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd) {
+                    double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd, const K1Exchange x) {
     constexpr int THREADS = K1BCfg<N>::THREADS;
     __shared__ double2 sA2[N * N];
     __shared__ double red[4 * (THREADS / 32)];
@@ -291,19 +336,21 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
         acc_im = dd_add_d(acc_im, wi);
     }
     block_reduce_dd(acc_re, acc_im, red);
-    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd);
+    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd, x);
 }
 
 // Sums the partials of several kernels (bulk + unaligned head / tail) in block order; one warp.
 __global__ void glynn_finish_kernel(const double *__restrict__ partials, int nblocks, int scale_log2,
-                                    double *__restrict__ out_dd) {
-    k1_sum_partials(partials, nblocks, scale_log2, out_dd);
+                                    double *__restrict__ out_dd, const K1Exchange x) {
+    double res[4];
+    k1_sum_partials(partials, nblocks, scale_log2, out_dd, res);
+    if (x.world > 0) k1_exchange(x, res);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host-side launch
 // ---------------------------------------------------------------------------------------------
-typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *, unsigned int *, double *);
+typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *, unsigned int *, double *, const K1Exchange);
 
 static k1_fn g_k1_fn[BP_MAX_N + 1], g_k1_bulk[BP_MAX_N + 1];
 static int g_k1_minb[BP_MAX_N + 1], g_k1_bulk_threads[BP_MAX_N + 1];
@@ -322,7 +369,7 @@ static cudaEvent_t g_const_event[64];
 static bool g_const_event_valid[64];
 
 static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_partials, int *grid_out,
-                      unsigned int *d_counter, double *d_out_dd) {
+                      unsigned int *d_counter, double *d_out_dd, const K1Exchange &x) {
     const uint64_t window = 1ull << K1_WINDOW_LOG2;
     const uint64_t total = hi - lo;
     const uint64_t max_threads = (uint64_t)h->sm_count * g_k1_minb[N] * K1_THREADS;
@@ -332,15 +379,20 @@ static int k1_generic(bp_context *h, const double *dA, int N, uint64_t lo, uint6
     uint64_t nthreads = (total + span - 1) / span;
     if (nthreads == 0) nthreads = 1;
     const int grid = (int)((nthreads + K1_THREADS - 1) / K1_THREADS);
-    g_k1_fn[N]<<<grid, K1_THREADS, 0, h->stream>>>(dA, lo, hi, span, d_partials, d_counter, d_out_dd);
+    g_k1_fn[N]<<<grid, K1_THREADS, 0, h->stream>>>(dA, lo, hi, span, d_partials, d_counter, d_out_dd, x);
     BP_CHECK_LAUNCH(h);
     *grid_out = grid;
     return BP_OK;
 }
 
-// Enqueue K1 over Gray steps [lo, hi) of an N x N device matrix; d_out_dd receives the
-// un-normalised double-double partial.
-int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_out_dd) {
+// c_A2 currently holds the image of this (handle, matrix, declared-resident generation); guarded by g_const_mutex
+struct K1ConstOwner { const bp_context *h; const double *dA; int N; uint64_t gen; };
+static K1ConstOwner g_const_owner[64];
+
+// Enqueue K1 over Gray steps [lo, hi) of an N x N device matrix; d_out_dd (may be NULL) receives the un-normalised
+// double-double partial.  d_exchange_out != NULL: the kernel that finishes the sum also runs the peer-memory exchange of the
+// handle (bp_exchange_*) and writes all ranks' partials there.
+int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t hi, double *d_out_dd, double *d_exchange_out) {
     static const bool ready = [] {   // thread-safe one-time registration of the template instances
         k1_entry<BP_MAX_N>(g_k1_fn, g_k1_minb, g_k1_bulk);
         if (const char *e = getenv("BP_K1_BULK_MAX_N"))   // tuning: generic kernel above this N
@@ -369,6 +421,18 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
     // one kernel covers the whole range (the usual case: full permanents and 64-aligned shards): its last block finishes
     const bool single = bulk ? (blo == lo && bhi == hi) : (hi > lo);
     unsigned int *d_counter = single ? h->d_counter : nullptr;
+    K1Exchange none, xchg;
+    none.world = 0; none.rank = 0; none.seq = 0; none.out_all = nullptr;
+    xchg = none;
+    if (d_exchange_out) {
+        if (h->xchg_world < 1) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_exchange: call bp_exchange_create / bp_exchange_connect first");
+        for (int r = 0; r < h->xchg_world; ++r) {
+            if (!h->xchg_peer[r]) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_exchange: rank %d is not connected", r);
+            xchg.peer[r] = h->xchg_peer[r];
+        }
+        xchg.world = h->xchg_world; xchg.rank = h->xchg_rank; xchg.seq = ++h->xchg_seq; xchg.out_all = d_exchange_out;
+    }
+    const K1Exchange &xs = single ? xchg : none;     // the exchange runs in whichever kernel finishes the sum
     if (bulk) {
         const size_t bytes = sizeof(double2) * (size_t)N * N;
         const uint64_t total = bhi - blo;
@@ -382,14 +446,22 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
         const int grid = (int)(((total + span - 1) / span + bthreads - 1) / bthreads);
         {
             std::lock_guard<std::mutex> g(g_const_mutex);
-            if (!g_const_event_valid[h->device]) {
-                BP_CUDA(h, cudaEventCreateWithFlags(&g_const_event[h->device], cudaEventDisableTiming));
-                g_const_event_valid[h->device] = true;
-            } else {
-                BP_CUDA(h, cudaStreamWaitEvent(h->stream, g_const_event[h->device], 0));   // previous user of c_A2
+            K1ConstOwner &own = g_const_owner[h->device];
+            // a matrix declared resident whose image is still the last one written: nothing to copy (and nothing to wait for --
+            // every launch that read or wrote c_A2 since then came from this handle's own stream)
+            const bool keep = g_const_event_valid[h->device] && h->resident_A == dA && own.h == h && own.dA == dA && own.N == N &&
+                              own.gen == h->resident_gen;
+            if (!keep) {
+                if (!g_const_event_valid[h->device]) {
+                    BP_CUDA(h, cudaEventCreateWithFlags(&g_const_event[h->device], cudaEventDisableTiming));
+                    g_const_event_valid[h->device] = true;
+                } else {
+                    BP_CUDA(h, cudaStreamWaitEvent(h->stream, g_const_event[h->device], 0));   // previous user of c_A2
+                }
+                BP_CUDA(h, cudaMemcpyToSymbolAsync(c_A2, dA, bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
+                own.h = h; own.dA = dA; own.N = N; own.gen = (h->resident_A == dA) ? h->resident_gen : ~0ull;
             }
-            BP_CUDA(h, cudaMemcpyToSymbolAsync(c_A2, dA, bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
-            g_k1_bulk[N]<<<grid, bthreads, 0, h->stream>>>(dA, blo, bhi, span, d_partials, d_counter, d_out_dd);
+            g_k1_bulk[N]<<<grid, bthreads, 0, h->stream>>>(dA, blo, bhi, span, d_partials, d_counter, d_out_dd, xs);
             BP_CHECK_LAUNCH(h);
             BP_CUDA(h, cudaEventRecord(g_const_event[h->device], h->stream));
         }
@@ -397,20 +469,20 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
     }
     if (blo > lo) {   // head (everything when the bulk path is not taken)
         int g = 0;
-        if ((rc = k1_generic(h, dA, N, lo, blo, d_partials + 4 * nparts, &g, d_counter, d_out_dd))) return rc;
+        if ((rc = k1_generic(h, dA, N, lo, blo, d_partials + 4 * nparts, &g, d_counter, d_out_dd, xs))) return rc;
         nparts += g;
     }
     if (hi > bhi) {   // tail
         int g = 0;
-        if ((rc = k1_generic(h, dA, N, bhi, hi, d_partials + 4 * nparts, &g, nullptr, d_out_dd))) return rc;
+        if ((rc = k1_generic(h, dA, N, bhi, hi, d_partials + 4 * nparts, &g, nullptr, d_out_dd, none))) return rc;
         nparts += g;
     }
-    if (nparts == 0) {   // empty range
-        BP_CUDA(h, cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 4, h->stream));
+    if (nparts == 0 && !d_exchange_out) {   // empty range
+        if (d_out_dd) BP_CUDA(h, cudaMemsetAsync(d_out_dd, 0, sizeof(double) * 4, h->stream));
         return BP_OK;
     }
-    if (single) return BP_OK;   // the kernel's last block has written d_out_dd
-    glynn_finish_kernel<<<1, 32, 0, h->stream>>>(d_partials, nparts, N, d_out_dd);
+    if (single) return BP_OK;   // the kernel's last block has written d_out_dd (and exchanged it)
+    glynn_finish_kernel<<<1, 32, 0, h->stream>>>(d_partials, nparts, N, d_out_dd, xchg);   // (an empty range contributes zero)
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }

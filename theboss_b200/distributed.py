@@ -88,9 +88,10 @@ class ShardedGlynnPermanent:
 
     ``compute(A)`` takes a HOST matrix (the user-facing call: upload, K1 on this rank's Gray slice,
     all-gather of 32-byte partials, fixed-order sum); ``enqueue_resident()`` / ``finish()`` is the same
-    with the matrix already resident in HBM (bench.py's device-timed leg)."""
+    with the matrix already resident in HBM (bench.py's device-timed leg).  ``exchange``: "peer" (default; partials travel
+    through peer memory inside the K1 kernel, falling back to NCCL when the GPUs cannot map each other) or "nccl"."""
 
-    def __init__(self, N: int, device: Optional[int] = None, group=None):
+    def __init__(self, N: int, device: Optional[int] = None, group=None, exchange: str = "peer"):
         import torch
         import torch.distributed as dist
 
@@ -104,6 +105,7 @@ class ShardedGlynnPermanent:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.lo, self.hi = gray_shard(self.N, self.world_size, self.rank)
         stream = torch.cuda.current_stream(self.device)
+        self._stream_ptr = stream.cuda_stream
         self.handle = _native.Handle(self.device, stream_ptr=stream.cuda_stream)
         dev = torch.device("cuda", self.device)
         self.d_A = torch.zeros(self.N * self.N * 2, dtype=torch.float64, device=dev)
@@ -111,15 +113,49 @@ class ShardedGlynnPermanent:
         self.d_all = torch.zeros(4 * self.world_size, dtype=torch.float64, device=dev)
         self.h_A = torch.zeros(self.N * self.N * 2, dtype=torch.float64).pin_memory()
         self.h_all = torch.zeros(4 * self.world_size, dtype=torch.float64).pin_memory()
+        self.handle.glynn_set_resident(self.d_A.data_ptr())
+        self.exchange = "none" if self.world_size == 1 else "nccl"
+        if self.world_size > 1 and exchange != "nccl":
+            self._connect_peer_exchange()
+
+    def _connect_peer_exchange(self) -> None:
+        """Partial exchange over peer memory (NVLink): the last block of K1 stores this rank's 32 bytes into every peer's slot
+        buffer and waits for theirs -- no NCCL launch per permanent.  Every rank must agree: if any rank cannot map a peer
+        (no peer access between the GPUs, IPC unavailable) all of them keep the NCCL all-gather."""
+        torch, dist = self._torch, self._dist
+        ok, handles = 1, None
+        try:
+            mine = self.handle.exchange_create(self.world_size, self.rank)
+            handles = [None] * self.world_size
+            dist.all_gather_object(handles, mine, group=self.group)
+            self.handle.exchange_connect(handles)
+        except Exception:   # noqa: BLE001 -- fall back together
+            ok = 0
+        on_gpu = dist.get_backend(self.group) != "gloo"      # (gloo: the two-process single-GPU test)
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", self.device) if on_gpu else torch.device("cpu"))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.exchange = "peer"
+        else:
+            try:
+                self.handle.exchange_destroy()
+            except Exception:   # noqa: BLE001
+                pass
 
     def upload(self, A: np.ndarray) -> None:
         A = np.ascontiguousarray(A, dtype=np.complex128)
         assert A.shape == (self.N, self.N)
         self.h_A.numpy()[:] = A.view(np.float64).reshape(-1)
         self.d_A.copy_(self.h_A, non_blocking=True)
+        self.handle.glynn_set_resident(self.d_A.data_ptr())     # new contents: the kernel's constant-bank image is rebuilt once
 
     def enqueue_resident(self) -> None:
         """K1 on this rank's slice + the partial exchange, all on the current stream, no host sync."""
+        assert self._torch.cuda.current_stream(self.device).cuda_stream == self._stream_ptr, (
+            "ShardedGlynnPermanent is bound to the torch stream that was current when it was built")
+        if self.exchange == "peer":
+            self.handle.glynn_matrix_range_exchange(self.d_A.data_ptr(), self.N, self.lo, self.hi, self.d_all.data_ptr())
+            return
         self.handle.glynn_matrix_range_dev(self.d_A.data_ptr(), self.N, self.lo, self.hi, self.d_part.data_ptr())
         if self.world_size > 1:
             self._dist.all_gather_into_tensor(self.d_all, self.d_part, group=self.group)
