@@ -462,7 +462,7 @@ def c5_legs(world, rank, local_rank, fp64_peak):
 
     from theboss_b200 import _native
     from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import prepare_interferometer_matrix_in_expanded_space
-    from theboss_b200.distributed import gather_samples, shard_bounds
+    from theboss_b200.distributed import dynamic_gccb_simulate, gather_samples, shard_bounds
 
     h = _native.default_handle(local_rank)
     dev = f"cuda:{local_rank}"
@@ -473,24 +473,34 @@ def c5_legs(world, rank, local_rank, fp64_peak):
     for name, matrix, state, eta, total, scaling in (
             ("uniform_eta0.5", U, s, 0.5, 10_000, "strong"),
             ("nonuniform_dilated", big, s_big, -1.0, 1250 * world, "weak")):
+        dynamic = eta < 0 and world > 1
         lo, hi = shard_bounds(total, world, rank)
         h.gccb_simulate(matrix, state, min(hi - lo, 64), eta=eta, seed=2, first_sample=lo)      # warm-up (scratch allocation)
-        best_ms, local, launches = None, None, 0
+        best_ms, local, launches, everything, drawn = None, None, 0, None, hi - lo
         for _ in range(2 if eta >= 0 else 1):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             l0 = h.launch_count()
-            h.timer_start()
-            local = h.gccb_simulate(matrix, state, hi - lo, eta=eta, seed=5, first_sample=lo)
-            ms = h.timer_stop()
+            if dynamic:
+                # per-sample cost varies by orders of magnitude: batches of 64 samples handed out on demand (shared counter in
+                # the process group's store); this rank's device time = the sum over its bp_gccb_simulate calls
+                tm = []
+                everything = dynamic_gccb_simulate(matrix, state, total, eta=eta, seed=5, device=local_rank, batch=64, timer=tm)
+                ms, drawn = tm[0], int(tm[1])
+            else:
+                h.timer_start()
+                local = h.gccb_simulate(matrix, state, hi - lo, eta=eta, seed=5, first_sample=lo)
+                ms = h.timer_stop()
             launches = h.launch_count() - l0
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             best_ms = float(t.item()) if best_ms is None else min(best_ms, float(t.item()))
-        everything = gather_samples(torch.from_numpy(local).to(dev)).cpu().numpy()
-        leg = {"samples": total, "scaling": scaling, "ms": best_ms, "samples_per_s": total / (best_ms * 1e-3), "gpu_launches": int(launches)}
+        if not dynamic:
+            everything = gather_samples(torch.from_numpy(local).to(dev)).cpu().numpy()
+        leg = {"samples": total, "scaling": scaling, "ms": best_ms, "samples_per_s": total / (best_ms * 1e-3), "gpu_launches": int(launches),
+               "distribution": "batches of 64 samples on demand (shared counter), rank 0 drew %d" % drawn if dynamic else "contiguous slices"}
         if rank == 0:
             counts = everything.sum(axis=1)
             leg["particles_conserved"] = bool(everything.shape[0] == total and (counts == 30).all()) if eta < 0 else \
@@ -503,7 +513,7 @@ def c5_legs(world, rank, local_rank, fp64_peak):
             else:
                 again = h.gccb_simulate(matrix, state, 4, eta=eta, seed=5, first_sample=total - 4)
                 leg["identical_to_single_gpu"] = bool(np.array_equal(again, everything[total - 4:]))
-                leg["identity_checked_on"] = "the last 4 samples of the job (drawn by the last rank)"
+                leg["identity_checked_on"] = "the last 4 samples of the job"
             leg["roofline"] = sampling_roofline(everything, best_ms, fp64_peak, world)
         out[name] = leg
     return out

@@ -59,3 +59,39 @@ def test_sharded_permanent_and_sample_gather_world2():
     assert np.array_equal(results[0][2], results[1][2])
     want = np.arange(35, dtype=np.int32).reshape(7, 5)
     assert np.array_equal(results[0][3], want) and np.array_equal(results[1][3], want)
+
+
+def _dynamic_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import handle_standin
+        from theboss_b200 import _native
+        from theboss_b200.distributed import dynamic_gccb_simulate
+        standin = handle_standin.OracleHandle()
+        _native.default_handle = lambda device=0: standin       # CPU stand-in of the device handle (test infrastructure)
+        U = workloads.haar(6, 3)
+        s = np.array([1, 1, 1, 0, 0, 0], dtype=np.int32)
+        got = dynamic_gccb_simulate(U, s, 37, seed=9, device=0, batch=5)
+        again = dynamic_gccb_simulate(U, s, 37, seed=9, device=0, batch=8)       # a second call uses a fresh counter
+        out_q.put((rank, got.copy(), again.copy(), standin.gccb_simulate(U, s, 37, seed=9)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_samples_handed_out_on_demand_equal_the_single_rank_run_world2():
+    """dynamic_gccb_simulate (batches of samples drawn from a shared counter in the process group's store): whatever rank draws
+    which batch, every rank ends with the array a single rank would have produced -- the generator is keyed by the global
+    sample index."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dynamic_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    results = sorted([q.get(timeout=180) for _ in range(world)], key=lambda x: x[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for _, got, again, single in results:
+        assert got.shape == (37, 6) and np.all(got.sum(axis=1) == 3)
+        assert np.array_equal(got, single) and np.array_equal(again, single)

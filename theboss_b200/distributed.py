@@ -205,3 +205,59 @@ def sharded_gccb_simulate(U, input_state, n_samples: int, eta: float = -1.0, see
         return local
     t = torch.from_numpy(local).to(torch.device("cuda", dev))
     return gather_samples(t, group).cpu().numpy()
+
+
+_dynamic_calls = 0
+
+
+def dynamic_gccb_simulate(U, input_state, n_samples: int, eta: float = -1.0, seed: int = 0, device: Optional[int] = None,
+                          group=None, batch: int = 64, timer=None):
+    """GCC-B sampling run whose samples are handed out to the ranks in batches of ``batch`` on demand (a shared counter in the
+    process group's store), for workloads whose per-sample cost varies by orders of magnitude -- the dilated lossy networks of
+    BASELINE config 5(ii), where a sample costs between ~1e6 and 3e11 flops depending on the outcome it happens to draw.  The
+    generator is keyed by the GLOBAL sample index, so the result is the same array as the single-GPU run whatever rank drew
+    which batch.  Returns the full (n_samples, m) int32 array on every rank (one all-reduce of the scattered rows at the end).
+    ``timer``: optional list that receives this rank's summed device time of its bp_gccb_simulate calls in milliseconds."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _native
+
+    global _dynamic_calls
+    _dynamic_calls += 1
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    dev = torch.cuda.current_device() if device is None else int(device)
+    Um = _native.as_matrix(U)
+    s = _native.as_state(input_state, Um.shape[0])
+    h = _native.default_handle(dev)
+    out = np.zeros((int(n_samples), Um.shape[0]), dtype=np.int32)
+    if world == 1:
+        if timer is not None:
+            h.timer_start()
+        out[:] = h.gccb_simulate(Um, s, n_samples, eta=eta, seed=seed)
+        if timer is not None:
+            timer.append(h.timer_stop())
+        return out
+    store = dist.distributed_c10d._get_default_store()
+    key = f"bossperm/dynamic/{_dynamic_calls}"
+    ms, mine = 0.0, 0
+    while True:
+        hi = int(store.add(key, int(batch)))            # atomic: the batch [hi - batch, hi) is this rank's
+        lo = hi - int(batch)
+        if lo >= n_samples:
+            break
+        hi = min(hi, int(n_samples))
+        if timer is not None:
+            h.timer_start()
+        out[lo:hi] = h.gccb_simulate(Um, s, hi - lo, eta=eta, seed=seed, first_sample=lo)
+        if timer is not None:
+            ms += h.timer_stop()
+        mine += hi - lo
+    if timer is not None:
+        timer.append(ms)
+        timer.append(mine)
+    on_gpu = dist.get_backend(group) != "gloo"          # (gloo: the CPU test of this scheduling logic)
+    t = torch.from_numpy(out).to(torch.device("cuda", dev)) if on_gpu else torch.from_numpy(out)
+    dist.all_reduce(t, group=group)                     # every row was written by exactly one rank, the others hold zeros
+    return t.cpu().numpy()
