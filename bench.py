@@ -300,6 +300,24 @@ def secondary_metrics(device):
         out["gccb_n20_m40"] = {"samples": 16384, "seconds": tg, "samples_per_s": 16384 / tg}
     except Exception as e:   # noqa: BLE001
         out["gccb_n24_m48"] = {"error": repr(e)}
+    try:   # BOBS (row f1 / f4): NonuniformLossesApproximationStrategy on the config-5 lossy network, n=30, m=60, half of the modes approximated
+        from theboss_b200.boson_sampling_utilities.permanent_calculators.ryser_permanent_calculator import RyserPermanentCalculator
+        from theboss_b200.simulation_strategies.nonuniform_losses_approximation_strategy import NonuniformLossesApproximationStrategy
+        U, U_lossy, s = workloads.c5_lossy(30, 60)
+        strat = NonuniformLossesApproximationStrategy(RyserPermanentCalculator(U_lossy, device=device), 30)
+        np.random.seed(11)
+        strat.simulate([int(x) for x in s], 16)
+        S_n = 256
+        t0 = time.perf_counter()
+        res = strat.simulate([int(x) for x in s], S_n)
+        t = time.perf_counter() - t0
+        out["bobs_nonuniform_n30_m60_k30"] = {"samples": S_n, "seconds": t, "samples_per_s": S_n / t,
+                                              "mean_particles_detected": float(np.mean([sum(x) for x in res])),
+                                              "h2d_bytes_per_sample": 16 * 30 + 4 * 120,
+                                              "note": "per-sample matrices (120 x 120 dilation) built on the device from template + phases + QFT; "
+                                                      "round 1 shipped 230 KB per sample"}
+    except Exception as e:   # noqa: BLE001
+        out["bobs_nonuniform_n30_m60_k30"] = {"error": repr(e)}
     try:   # C1: GCC (version A), n=5, m=10, 1000 samples through the strategy class
         from theboss_b200.boson_sampling_utilities.permanent_calculators.glynn_gray_permanent_calculator import GlynnGrayPermanentCalculator
         from theboss_b200.simulation_strategies.generalized_cliffords_simulation_strategy import GeneralizedCliffordsSimulationStrategy

@@ -186,6 +186,21 @@ int bp_gccb_simulate_batch(bp_handle h, const double *Us, int m, const int32_t *
                            uint64_t seed, int64_t first_sample, const double *tape, int tape_particles,
                            int32_t *out);
 
+/* The same, with the per-sample matrices built on the device instead of shipped (16 m^2 bytes per
+ * sample): sample i runs on
+ *     Us[i] = (B with its columns permuted by perms[i]) @ diag(phases[i], 1, ..., 1) @ (QFT on the first a modes),
+ * what NonuniformLossesApproximationStrategy builds per sample (M0 @ random_phases @ QFT in its 2m-mode dilation,
+ * nonuniform_losses_approximation_strategy.py:331-347: B = the dilation template, perms = NULL, a = approximated modes) and
+ * LossyStateApproximationSimulationStrategy (U[:, random permutation] @ random_phases @ QFT,
+ * lossy_state_approximated_simulation_strategy.py:329-362: B = U, a = m - hierarchy_level).
+ * B: [m][m] complex; qft: [a][a] complex; phases: [n_samples][a] complex (unit modulus); perms: [n_samples][m] column indices or NULL.
+ * bp_bobs_build returns the matrices themselves ([n_samples][m][m] complex) for inspection. */
+int bp_gccb_simulate_bobs(bp_handle h, const double *B, int m, const double *qft, int a, const double *phases,
+                          const int32_t *perms, const int32_t *states, int64_t n_samples, uint64_t seed,
+                          int64_t first_sample, const double *tape, int tape_particles, int32_t *out);
+int bp_bobs_build(bp_handle h, const double *B, int m, const double *qft, int a, const double *phases,
+                  const int32_t *perms, int64_t n_samples, double *Us_out);
+
 #ifdef __cplusplus
 }
 #endif

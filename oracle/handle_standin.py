@@ -108,6 +108,12 @@ class OracleHandle:
             out = orc.gccb_simulate(U, s, tape, precision=self._precision)
         return np.array(out, dtype=np.int32).reshape(int(n_samples), U.shape[0])
 
+    def gccb_simulate_bobs(self, B, qft, phases, perms, states, seed=0, first_sample=0, tape=None):
+        return self.gccb_simulate_batch(bobs_matrices(B, qft, phases, perms), states, seed=seed, first_sample=first_sample, tape=tape)
+
+    def bobs_build(self, B, qft, phases, perms=None):
+        return bobs_matrices(B, qft, phases, perms)
+
     def gccb_simulate_batch(self, Us, states, seed=0, first_sample=0, tape=None):
         """One GCC-B sample per (matrix, input state) pair through the oracle's sampling loop."""
         self.calls += 1
@@ -121,6 +127,23 @@ class OracleHandle:
                 row = tape[i:i + 1, : 1 + 2 * n]
                 out[i] = orc.gccb_simulate(Us[i], states[i], row, precision=self._precision)[0]
         return out
+
+
+def bobs_matrices(B, qft, phases, perms=None):
+    """NumPy restatement of the device-side BOBS matrix build (include/bossperm.h, bp_bobs_build):
+    Us[i] = (B[:, perms[i]]) @ diag(phases[i], 1 ...) @ (QFT on the first a modes)
+    -- nonuniform_losses_approximation_strategy.py:331-347, lossy_state_approximated_simulation_strategy.py:329-362."""
+    B = np.asarray(B, dtype=np.complex128)
+    phases = np.asarray(phases, dtype=np.complex128)
+    S, a = phases.shape
+    m = B.shape[0]
+    if perms is None:
+        Us = np.repeat(B[None, :, :], S, axis=0)
+    else:
+        Us = np.ascontiguousarray(np.transpose(B.T[np.asarray(perms)], (0, 2, 1)))
+    if a > 0:
+        Us[:, :, :a] = (Us[:, :, :a] * phases[:, None, :]) @ np.asarray(qft, dtype=np.complex128)
+    return Us
 
 
 def install(monkeypatch, precision: str = "d") -> OracleHandle:

@@ -114,3 +114,33 @@ def test_lossy_state_approximation_runs_and_conserves_particles():
     assert abs(out.sum(axis=1).mean() - 0.7 * 4) < 0.1       # Binomial(4, 0.7) particles survive on average
     full = np.array(LossyStateApproximationSimulationStrategy(calc, 1.0, 6).simulate(s, 50))
     assert np.all(full.sum(axis=1) == 4)
+
+
+@pytest.mark.parametrize("m,a,with_perms", [(6, 0, False), (6, 3, False), (12, 12, True), (9, 4, True), (40, 17, False), (120, 60, False)])
+def test_device_side_matrix_build_matches_the_reference_construction(handle, m, a, with_perms):
+    """Row f4: bp_bobs_build / bp_gccb_simulate_bobs build (B[:, perm]) @ diag(phases, 1 ...) @ QFT_a per sample on the device --
+    M0 @ random_phases @ QFT of nonuniform_losses_approximation_strategy.py:331-347 and U[:, perm] @ phases @ QFT of
+    lossy_state_approximated_simulation_strategy.py:329-362 -- checked against the NumPy restatement of those lines."""
+    from oracle.handle_standin import bobs_matrices
+    from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import generate_qft_matrix_for_first_m_modes
+    rng = np.random.RandomState(m * 31 + a)
+    S = 9
+    B = workloads.haar(m, m + a)
+    qft = generate_qft_matrix_for_first_m_modes(a, m)[:a, :a]
+    phases = np.exp(2j * np.pi * rng.rand(S, a))
+    perms = np.argsort(rng.rand(S, m), axis=1).astype(np.int32) if with_perms else None
+    got = handle.bobs_build(B, qft, phases, perms)
+    want = bobs_matrices(B, qft, phases, perms)
+    assert got.shape == want.shape == (S, m, m)
+    assert np.abs(got - want).max() <= 1e-13
+    assert np.array_equal(got[:, :, a:], want[:, :, a:])                        # untouched columns are copies
+    # the sampler on device-built matrices == the sampler on the same matrices shipped from the host (same decision tape)
+    if m <= 12:
+        states = np.zeros((S, m), dtype=np.int32)
+        for i in range(S):
+            for j in rng.randint(0, m, rng.randint(0, 5)):
+                states[i, j] += 1
+        tape = rng.random_sample((S, 1 + 2 * max(1, int(states.sum(axis=1).max()))))
+        a_dev = handle.gccb_simulate_bobs(B, qft, phases, perms, states, tape=tape)
+        a_host = handle.gccb_simulate_batch(got, states, tape=tape)
+        assert np.array_equal(a_dev, a_host)

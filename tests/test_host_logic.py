@@ -350,7 +350,8 @@ def test_bench_flop_accounting_of_a_sampling_run_matches_the_true_draw_order():
 
 
 def test_bobs_per_sample_matrices_and_slicing(monkeypatch):
-    """What the two BOBS strategies hand to bp_gccb_simulate_batch: every per-sample matrix must be what the reference
+    """What the two BOBS strategies hand to bp_gccb_simulate_bobs: every per-sample matrix (rebuilt here from the operands with the
+    NumPy restatement of the device build) must be what the reference
     builds -- M0 @ diag(phases) @ QFT in the top-left block of an isometric 2m-mode dilation
     (nonuniform_losses_approximation_strategy.py:331-347), resp. a column-permuted unitary times phases times QFT
     (lossy_state_approximated_simulation_strategy.py:329-362) -- although only the columns that change are recomputed per
@@ -364,9 +365,11 @@ def test_bobs_per_sample_matrices_and_slicing(monkeypatch):
         NonuniformLossesApproximationStrategy)
     calls = []
 
+    from oracle.handle_standin import bobs_matrices
+
     class Capture:
-        def gccb_simulate_batch(self, Us, states, seed=0, first_sample=0, tape=None):
-            calls.append((np.array(Us), np.array(states), seed, first_sample))
+        def gccb_simulate_bobs(self, B, qft, phases, perms, states, seed=0, first_sample=0, tape=None):
+            calls.append((bobs_matrices(B, qft, phases, perms), np.array(states), seed, first_sample))
             return np.array(states, dtype=np.int32)          # echo: lets the test see which rows came from which slice
 
     monkeypatch.setattr(_native, "default_handle", lambda device=0: Capture())
@@ -380,7 +383,7 @@ def test_bobs_per_sample_matrices_and_slicing(monkeypatch):
     for k in (0, 2, 6):
         calls.clear()
         strat = NonuniformLossesApproximationStrategy(Calc(lossy.copy(), s), k)
-        monkeypatch.setattr(strat, "_SLICE_BYTES", 16 * 4 * m * m * 8)              # 8 samples per slice
+        monkeypatch.setattr(strat, "_SLICE_SAMPLES", 8)                              # 8 samples per slice
         np.random.seed(k)
         out = strat.simulate(s, 20)
         assert [c[0].shape[0] for c in calls] == [8, 8, 4] and [c[3] for c in calls] == [0, 8, 16]
@@ -400,7 +403,7 @@ def test_bobs_per_sample_matrices_and_slicing(monkeypatch):
     for hl in (0, 2, 6):
         calls.clear()
         strat = LossyStateApproximationSimulationStrategy(Calc(U.copy(), s), 0.6, hl)
-        monkeypatch.setattr(strat, "_SLICE_BYTES", 16 * m * m * 8)
+        monkeypatch.setattr(strat, "_SLICE_SAMPLES", 8)
         np.random.seed(hl)
         strat.simulate(s, 20)
         assert [c[0].shape[0] for c in calls] == [8, 8, 4] and [c[3] for c in calls] == [0, 8, 16]
@@ -475,6 +478,9 @@ def test_every_entry_point_rejects_a_null_handle_without_touching_the_device():
         "bp_gccb_pmf": lambda: lib.bp_gccb_pmf(None, A.ctypes.data, 2, s.ctypes.data, s.ctypes.data, pmf.ctypes.data, None),
         "bp_gccb_simulate": lambda: lib.bp_gccb_simulate(None, A.ctypes.data, 2, s.ctypes.data, 1, -1.0, 0, 0, None, oi.ctypes.data),
         "bp_gccb_simulate_batch": lambda: lib.bp_gccb_simulate_batch(None, A.ctypes.data, 2, s.ctypes.data, 1, 0, 0, None, 0, oi.ctypes.data),
+        "bp_gccb_simulate_bobs": lambda: lib.bp_gccb_simulate_bobs(None, A.ctypes.data, 2, A.ctypes.data, 2, A.ctypes.data, None, s.ctypes.data, 1, 0, 0,
+                                                                   None, 0, oi.ctypes.data),
+        "bp_bobs_build": lambda: lib.bp_bobs_build(None, A.ctypes.data, 2, A.ctypes.data, 2, A.ctypes.data, None, 1, o.ctypes.data),
     }
     declared = set(_header_symbols()) - {"bp_abi_version", "bp_create", "bp_create_on_stream", "bp_destroy", "bp_last_error", "bp_launch_count"}
     assert declared == set(calls), declared ^ set(calls)

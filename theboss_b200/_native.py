@@ -61,6 +61,9 @@ SIGNATURES = {
     "bp_gccb_pmf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bp_gccb_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bp_gccb_simulate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "bp_gccb_simulate_bobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "bp_bobs_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 _lib = None
@@ -322,6 +325,57 @@ class Handle:
         self._call("bp_gccb_simulate_batch", Us.ctypes.data, m, states.ctypes.data, S, int(seed) & (2 ** 64 - 1),
                                                      int(first_sample), tp, tn, out.ctypes.data)
         return out
+
+    def gccb_simulate_bobs(self, B, qft, phases, perms, states, seed: int = 0, first_sample: int = 0,
+                           tape: Optional[np.ndarray] = None) -> np.ndarray:
+        """One GCC-B sample per row of ``states`` on the matrix (B[:, perms[i]]) @ diag(phases[i], 1...) @ QFT_a built on the
+        device (what the BOBS strategies construct per sample; see include/bossperm.h)."""
+        B, qft, a, phases, perms, S = _bobs_operands(B, qft, phases, perms)
+        m = B.shape[0]
+        states = np.ascontiguousarray(states, dtype=np.int32)
+        if states.shape != (S, m):
+            raise AttributeError("states must be (S, m)")
+        out = np.zeros((S, m), dtype=np.int32)
+        tp, tn = None, 0
+        if tape is not None:
+            tape = np.ascontiguousarray(tape, dtype=np.float64)
+            tn = (tape.shape[1] - 1) // 2
+            if tape.shape[0] != S or tape.shape[1] != 1 + 2 * tn or tn < int(states.sum(axis=1).max(initial=0)):
+                raise ValueError("decision tape must have shape (S, 1 + 2 * n_max)")
+            tp = tape.ctypes.data
+        self._call("bp_gccb_simulate_bobs", B.ctypes.data, m, qft.ctypes.data if a else None, a, phases.ctypes.data if a else None,
+                   perms.ctypes.data if perms is not None else None, states.ctypes.data, S, int(seed) & (2 ** 64 - 1),
+                   int(first_sample), tp, tn, out.ctypes.data)
+        return out
+
+    def bobs_build(self, B, qft, phases, perms=None) -> np.ndarray:
+        """The per-sample matrices of gccb_simulate_bobs themselves, (S, m, m) complex128, built on the device."""
+        B, qft, a, phases, perms, S = _bobs_operands(B, qft, phases, perms)
+        m = B.shape[0]
+        out = np.zeros((S, m, m), dtype=np.complex128)
+        self._call("bp_bobs_build", B.ctypes.data, m, qft.ctypes.data if a else None, a, phases.ctypes.data if a else None,
+                   perms.ctypes.data if perms is not None else None, S, out.ctypes.data)
+        return out
+
+
+def _bobs_operands(B, qft, phases, perms):
+    """Normalised operands of the device-side BOBS matrix build (include/bossperm.h): (B, qft, a, phases, perms, S)."""
+    B = as_matrix(B)
+    if B.shape[0] != B.shape[1]:
+        raise AttributeError("B must be square")
+    m = B.shape[0]
+    phases = np.ascontiguousarray(phases, dtype=np.complex128)
+    if phases.ndim != 2:
+        raise AttributeError("phases must be (S, a)")
+    S, a = phases.shape
+    qft = np.ascontiguousarray(qft, dtype=np.complex128)
+    if qft.shape != (a, a) or a > m:
+        raise AttributeError("qft must be (a, a) with a <= m")
+    if perms is not None:
+        perms = np.ascontiguousarray(perms, dtype=np.int32)
+        if perms.shape != (S, m) or (S and (perms.min() < 0 or perms.max() >= m)):
+            raise AttributeError("perms must be (S, m) column indices")
+    return B, qft, a, phases, perms, S
 
 
 _default_handles = {}

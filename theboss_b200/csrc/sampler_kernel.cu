@@ -101,6 +101,58 @@ __global__ void k4_output_kernel(const unsigned char *__restrict__ occ_t, long l
     if (i < count) out[i] = (int)occ_t[i];
 }
 
+// Per-sample matrices of the BOBS strategies, built where they are used (row f4 of SURVEY.md section 8):
+//   Us[s][r][c] = B[r][perm_s(c)]                                          for c >= a
+//   Us[s][r][c] = sum_{q < a} B[r][perm_s(q)] * phase_s[q] * QFT[q][c]      for c <  a
+// i.e. (B with its columns permuted) @ diag(phases, 1 ...) @ (QFT on the first a modes) --
+// nonuniform_losses_approximation_strategy.py:331-347 (B = dilation template, no permutation, a = approximated modes) and
+// lossy_state_approximated_simulation_strategy.py:329-362 (B = the unitary, one column permutation per sample).
+// One block per sample; a row's phased entries are staged in shared memory, the QFT comes through L1/L2.
+__global__ void __launch_bounds__(256) k4_bobs_build_kernel(const double2 *__restrict__ B, int m, const double2 *__restrict__ qft, int a,
+                                                            const double2 *__restrict__ phases, const int *__restrict__ perms,
+                                                            double2 *__restrict__ Us) {
+    extern __shared__ double2 bb_t[];                    // [rows_per_pass][a]
+    const long long smp = blockIdx.x;
+    const double2 *ph = phases + smp * a;
+    const int *perm = perms ? perms + smp * m : nullptr;
+    double2 *out = Us + smp * (long long)m * m;
+    const int rows_per_pass = a > 0 ? max(1, min(m, 2048 / a)) : m;
+    for (int r0 = 0; r0 < m; r0 += rows_per_pass) {
+        const int nr = min(rows_per_pass, m - r0);
+        for (int e = threadIdx.x; e < nr * a; e += blockDim.x) {
+            const int r = e / a, q = e - r * a;
+            const double2 b = B[(long long)(r0 + r) * m + (perm ? perm[q] : q)], p = ph[q];
+            bb_t[e] = make_double2(b.x * p.x - b.y * p.y, b.x * p.y + b.y * p.x);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * m; e += blockDim.x) {
+            const int r = e / m, c = e - r * m;
+            double2 v;
+            if (c >= a) v = B[(long long)(r0 + r) * m + (perm ? perm[c] : c)];
+            else {
+                double re = 0.0, im = 0.0;
+                const double2 *t = bb_t + r * a;
+                for (int q = 0; q < a; ++q) {
+                    const double2 x = t[q], w = qft[q * a + c];
+                    re = fma(x.x, w.x, re); re = fma(-x.y, w.y, re);
+                    im = fma(x.x, w.y, im); im = fma(x.y, w.x, im);
+                }
+                v = make_double2(re, im);
+            }
+            out[(long long)(r0 + r) * m + c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+struct BobsBuild {             // host description of a device-side matrix build (all pointers HOST memory)
+    const double *B;           // [m][m] complex
+    const double *qft;         // [a][a] complex
+    int a;
+    const double *phases;      // [n_samples][a] complex
+    const int32_t *perms;      // [n_samples][m] or NULL
+};
+
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
@@ -112,6 +164,31 @@ static int occ_to_u8(bp_context *h, const int32_t *v, int m, unsigned char *dst,
         n += v[i];
     }
     *sum = n;
+    return BP_OK;
+}
+
+// Device-side build of S per-sample matrices (samples [done, done + S) of the request) into dU.  d_B / d_qft: the resident
+// operands (uploaded once per request by bobs_upload_resident), scratch slot MISC: this batch's phases and permutations.
+static int bobs_upload_resident(bp_context *h, const BobsBuild &bb, int m, double *d_B, double *d_qft) {
+    BP_CUDA(h, cudaMemcpyAsync(d_B, bb.B, sizeof(double) * 2 * (size_t)m * m, cudaMemcpyHostToDevice, h->stream));
+    if (bb.a > 0) BP_CUDA(h, cudaMemcpyAsync(d_qft, bb.qft, sizeof(double) * 2 * (size_t)bb.a * bb.a, cudaMemcpyHostToDevice, h->stream));
+    return BP_OK;
+}
+static int bobs_build_batch(bp_context *h, const BobsBuild &bb, int m, long long done, long long S, const double *d_B,
+                            const double *d_qft, double *dU) {
+    const size_t ph_bytes = sizeof(double) * 2 * (size_t)S * (size_t)(bb.a > 0 ? bb.a : 1);
+    const size_t pm_bytes = bb.perms ? sizeof(int) * (size_t)S * m : 0;
+    int rc = bp_reserve(h, BP_SLOT_MISC, ((ph_bytes + 15) / 16) * 16 + pm_bytes + 64);
+    if (rc) return rc;
+    double *d_ph = (double *)h->d_buf[BP_SLOT_MISC];
+    int *d_pm = bb.perms ? (int *)((char *)d_ph + ((ph_bytes + 15) / 16) * 16) : nullptr;
+    if (bb.a > 0) BP_CUDA(h, cudaMemcpyAsync(d_ph, bb.phases + (size_t)done * 2 * bb.a, sizeof(double) * 2 * (size_t)S * bb.a, cudaMemcpyHostToDevice, h->stream));
+    if (bb.perms) BP_CUDA(h, cudaMemcpyAsync(d_pm, bb.perms + (size_t)done * m, pm_bytes, cudaMemcpyHostToDevice, h->stream));
+    const int rows_per_pass = bb.a > 0 ? ((2048 / bb.a) < 1 ? 1 : ((2048 / bb.a) > m ? m : (2048 / bb.a))) : m;
+    const size_t smem = sizeof(double) * 2 * (size_t)rows_per_pass * (size_t)(bb.a > 0 ? bb.a : 1);
+    k4_bobs_build_kernel<<<(unsigned)S, 256, smem, h->stream>>>((const double2 *)d_B, m, (const double2 *)d_qft, bb.a, (const double2 *)d_ph,
+                                                               d_pm, (double2 *)dU);
+    BP_CHECK_LAUNCH(h);
     return BP_OK;
 }
 
@@ -195,8 +272,8 @@ int bp_gccb_pmf(bp_handle h, const double *U, int m, const int32_t *s, const int
 // BOBS strategies draw a new matrix and a new lossy input state for every sample).
 static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32_t *s, bool per_sample, int64_t n_samples,
                               double eta, uint64_t seed, int64_t first_sample, const double *tape, int tape_n,
-                              int32_t *out, const char *who) {
-    if (!h || !U || !s || !out) return bp_fail(h, BP_ERR_INVALID, "%s: NULL argument", who);
+                              int32_t *out, const char *who, const BobsBuild *bb = nullptr) {
+    if (!h || (!U && !bb) || !s || !out) return bp_fail(h, BP_ERR_INVALID, "%s: NULL argument", who);
     if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: m=%d outside [1, %d]", who, m, BP_MAX_MODES);
     if (n_samples < 0) return bp_fail(h, BP_ERR_INVALID, "%s: n_samples=%lld", who, (long long)n_samples);
     if (eta > 1.0) return bp_fail(h, BP_ERR_INVALID, "%s: eta=%g > 1", who, eta);
@@ -247,7 +324,8 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
     // (launch slot -> sample through `order`, samples sorted by their step count, longest first).
     const bool ragged = per_sample || eta >= 0.0;
     const size_t state_bytes = (size_t)batch * (2 * (size_t)m + (size_t)n + 20) + u_count * (size_t)m + (size_t)m + 256 + 16;
-    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub * u_count + sizeof(double) * (size_t)(n + 2)))) return rc;
+    const size_t bb_bytes = bb ? ub + sizeof(double) * 2 * (size_t)bb->a * bb->a + 32 : 0;
+    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub * u_count + sizeof(double) * (size_t)(n + 4) + bb_bytes))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_STATE, state_bytes))) return rc;
     if ((rc = bp_reserve(h, BP_SLOT_TAPE, sizeof(double) * (size_t)batch * stride))) return rc;
     if (!ragged && (rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)maxW * max_chunks * (size_t)batch))) return rc;
@@ -256,6 +334,8 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
 
     double *dU = (double *)h->d_buf[BP_SLOT_AUX];
     double *d_w = dU + 2 * (size_t)m * m * u_count;
+    double *d_B = d_w + ((n + 3) & ~1), *d_qft = d_B + 2 * (size_t)m * m;   // resident operands of the device-side matrix build (16-byte aligned)
+    if (bb && (rc = bobs_upload_resident(h, *bb, m, d_B, d_qft))) return rc;
     if (!per_sample) BP_CUDA(h, cudaMemcpyAsync(dU, U, ub, cudaMemcpyHostToDevice, h->stream));
     if (eta >= 0.0) BP_CUDA(h, cudaMemcpyAsync(d_w, weights.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     // state carve-up: 8-byte and 4-byte items first (alignment), then bytes
@@ -280,7 +360,8 @@ static int gccb_simulate_impl(bp_context *h, const double *U, int m, const int32
         const long long S = (n_samples - done < batch) ? (n_samples - done) : batch;
         BP_CUDA(h, cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
         if (per_sample) {
-            BP_CUDA(h, cudaMemcpyAsync(dU, U + (size_t)done * 2 * m * m, ub * (size_t)S, cudaMemcpyHostToDevice, h->stream));
+            if (bb) { if ((rc = bobs_build_batch(h, *bb, m, done, S, d_B, d_qft, dU))) return rc; }
+            else BP_CUDA(h, cudaMemcpyAsync(dU, U + (size_t)done * 2 * m * m, ub * (size_t)S, cudaMemcpyHostToDevice, h->stream));
             BP_CUDA(h, cudaMemcpyAsync(d_s0, s8.data() + (size_t)done * m, (size_t)S * m, cudaMemcpyHostToDevice, h->stream));
         }
         if (tape) {
@@ -364,6 +445,52 @@ int bp_gccb_simulate_batch(bp_handle h, const double *Us, int m, const int32_t *
         return gccb_simulate_impl(h, Us, m, states, true, n_samples, -1.0, seed, first_sample, tape, tape ? tape_particles : 0, out,
                                   "bp_gccb_simulate_batch");
     });
+}
+
+static int bobs_check(bp_context *h, const double *B, int m, const double *qft, int a, const double *phases, int64_t n, const char *who) {
+    if (!h || !B) return bp_fail(h, BP_ERR_INVALID, "%s: NULL argument", who);
+    if (m < 1 || m > BP_MAX_MODES) return bp_fail(h, BP_ERR_UNSUPPORTED, "%s: m=%d outside [1, %d]", who, m, BP_MAX_MODES);
+    if (a < 0 || a > m) return bp_fail(h, BP_ERR_INVALID, "%s: a=%d outside [0, m=%d]", who, a, m);
+    if (a > 0 && (!qft || (n > 0 && !phases))) return bp_fail(h, BP_ERR_INVALID, "%s: NULL qft / phases with a=%d", who, a);
+    if (n < 0) return bp_fail(h, BP_ERR_INVALID, "%s: n_samples=%lld", who, (long long)n);
+    return BP_OK;
+}
+
+int bp_gccb_simulate_bobs(bp_handle h, const double *B, int m, const double *qft, int a, const double *phases, const int32_t *perms,
+                          const int32_t *states, int64_t n_samples, uint64_t seed, int64_t first_sample, const double *tape,
+                          int tape_particles, int32_t *out) {
+    int rc = bobs_check(h, B, m, qft, a, phases, n_samples, "bp_gccb_simulate_bobs");
+    if (rc) return rc;
+    if (tape && tape_particles < 0) return bp_fail(h, BP_ERR_INVALID, "bp_gccb_simulate_bobs: tape_particles=%d", tape_particles);
+    return no_throw(h, "bp_gccb_simulate_bobs", [&] {
+        BobsBuild bb = {B, qft, a, phases, perms};
+        return gccb_simulate_impl(h, nullptr, m, states, true, n_samples, -1.0, seed, first_sample, tape, tape ? tape_particles : 0, out,
+                                  "bp_gccb_simulate_bobs", &bb);
+    });
+}
+
+int bp_bobs_build(bp_handle h, const double *B, int m, const double *qft, int a, const double *phases, const int32_t *perms,
+                  int64_t n_samples, double *Us_out) {
+    int rc = bobs_check(h, B, m, qft, a, phases, n_samples, "bp_bobs_build");
+    if (rc) return rc;
+    if (!Us_out) return bp_fail(h, BP_ERR_INVALID, "bp_bobs_build: NULL argument");
+    if (n_samples == 0) return BP_OK;
+    BP_ON_DEVICE(h);
+    const size_t ub = sizeof(double) * 2 * (size_t)m * m;
+    long long batch = (long long)((256ull << 20) / ub);
+    if (batch < 1) batch = 1;
+    if (batch > n_samples) batch = n_samples;
+    if ((rc = bp_reserve(h, BP_SLOT_AUX, ub * (size_t)batch + ub + sizeof(double) * 2 * (size_t)a * a + 64))) return rc;
+    double *dU = (double *)h->d_buf[BP_SLOT_AUX], *d_B = dU + 2 * (size_t)m * m * (size_t)batch, *d_qft = d_B + 2 * (size_t)m * m;
+    BobsBuild bb = {B, qft, a, phases, perms};
+    if ((rc = bobs_upload_resident(h, bb, m, d_B, d_qft))) return rc;
+    for (long long done = 0; done < n_samples; done += batch) {
+        const long long S = n_samples - done < batch ? n_samples - done : batch;
+        if ((rc = bobs_build_batch(h, bb, m, done, S, d_B, d_qft, dU))) return rc;
+        BP_CUDA(h, cudaMemcpyAsync(Us_out + (size_t)done * 2 * m * m, dU, ub * (size_t)S, cudaMemcpyDeviceToHost, h->stream));
+        BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return BP_OK;
 }
 
 }  // extern "C"

@@ -6,8 +6,8 @@ reference draws a lossy input state -- the first ``hierarchy_level`` modes keep 
 eta (:96-138, :312-327), the remaining (approximated) modes are replaced by l ~ Binomial(n_approx, eta)
 particles in the first approximated mode (:170-203) -- and a matrix ``U[:, random permutation] @ random_phases @
 QFT`` acting on the approximated modes (:329-362), then takes ONE lossless GCC-B sample in a spawn process pool
-(:287-310).  Here the per-sample inputs and matrices are built vectorised on the host and go through batched device
-calls (``bp_gccb_simulate_batch``), one per slice of at most 256 MiB of matrices.
+(:287-310).  Here the per-sample inputs, phases and column permutations are drawn vectorised on the host; the matrices are built on the
+device (``bp_gccb_simulate_bobs``) and sampled by the batched device loop, one request per slice of samples.
 
 Deviation: the not-approximated part is thinned particle by particle (Binomial(s_i, eta) per mode), which equals
 the reference's weights for collision-free inputs and stays normalised for bunched ones (the reference's weights
@@ -31,8 +31,8 @@ class LossyStateApproximationSimulationStrategy(SimulationStrategyInterface):
         self._threads_number = threads_number                     # signature parity; the GPU batches instead
         self._device = getattr(bs_permanent_calculator, "device", 0)
 
-    #: host memory bound of one device request (bytes of per-sample matrices built and shipped at a time)
-    _SLICE_BYTES = 256 << 20
+    #: samples per device request (host arrays of one slice: states, phases, permutations)
+    _SLICE_SAMPLES = 65536
 
     def simulate(self, input_state: Sequence[int], samples_number: int = 1) -> List[Tuple[int, ...]]:
         if samples_number < 1:
@@ -46,7 +46,7 @@ class LossyStateApproximationSimulationStrategy(SimulationStrategyInterface):
         qft_a = generate_qft_matrix_for_first_m_modes(a, m)[:a, :a]
         seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
         handle = _native.default_handle(self._device)
-        step = max(1, min(total, self._SLICE_BYTES // (16 * m * m)))
+        step = max(1, min(total, self._SLICE_SAMPLES))
         out = np.zeros((total, m), dtype=np.int32)
         for lo in range(0, total, step):
             S = min(step, total - lo)
@@ -55,9 +55,7 @@ class LossyStateApproximationSimulationStrategy(SimulationStrategyInterface):
             if hl < m:
                 states[:, hl] = np.random.binomial(int(state[hl:].sum()), eta, S)
             phases = np.exp(2j * np.pi * np.random.rand(S, a))
-            perms = np.argsort(np.random.rand(S, m), axis=1)                      # one column permutation per sample
-            Us = np.ascontiguousarray(np.transpose(U.T[perms], (0, 2, 1)))        # Us[s] = U[:, perms[s]]
-            if a > 0:                                                             # only the first a columns meet the phases and the QFT
-                Us[:, :, :a] = (Us[:, :, :a] * phases[:, None, :]) @ qft_a
-            out[lo:lo + S] = handle.gccb_simulate_batch(Us, states, seed=seed, first_sample=lo)
+            perms = np.argsort(np.random.rand(S, m), axis=1).astype(np.int32)     # one column permutation per sample
+            # Us[s] = U[:, perms[s]] @ diag(phases_s, 1 ...) @ QFT_a, built on the device
+            out[lo:lo + S] = handle.gccb_simulate_bobs(U, qft_a, phases, perms, states, seed=seed, first_sample=lo)
         return [tuple(row) for row in out.tolist()]
