@@ -160,6 +160,12 @@ __host__ __device__ inline double guan_terms_of(const unsigned char *occ, int m)
     return full / (double)(best_w + 1) * (double)((best_w >> 1) + 1);
 }
 
+// 1 / q for q = 1 .. 41 (entry 0 unused): reciprocals of the step denominators of guan_step
+static __constant__ double gw_rcp[BP_MAX_N + 2] = {
+    0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14,
+    1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27,
+    1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41};
+
 struct GuanState {                // per-thread
     unsigned long long dirmask;   // bit v set: digit v currently moves downwards
     double binom;                 // prod_v C(w_v, r_v) * (top weight 1 or 2), exact integer
@@ -217,11 +223,13 @@ __device__ __forceinline__ int guan_step(const GuanItem &it, unsigned char *r, G
     delta = dir;
     const int w = it.mult[v];
     if (w > 1) {
-        // C(w, nxt) from C(w, cur): exact integer arithmetic in doubles (values < 2^51)
+        // C(w, nxt) from C(w, cur): exact integer arithmetic in doubles (values < 2^46).  The quotient is an integer, so the
+        // division is a multiplication by the rounded reciprocal followed by rint (error < 2^46 * 2^-52: the nearest integer
+        // is the exact quotient) -- no FP64 division sequence at the period boundaries of the term loops.
         double b = st.binom;
-        if (v == it.D - 1) b /= gw_top_weight(it, cur);   // divide by 1 or 2: exact
-        if (dir > 0) b = rint(b * (double)(w - cur) / (double)nxt);
-        else         b = rint(b * (double)cur / (double)(w - nxt));
+        if (v == it.D - 1) b *= (2 * cur < w) ? 0.5 : 1.0;   // divide by the top weight (2 or 1): exact
+        if (dir > 0) b = rint(b * (double)(w - cur) * gw_rcp[nxt]);
+        else         b = rint(b * (double)cur * gw_rcp[w - nxt]);
         if (v == it.D - 1) b *= gw_top_weight(it, nxt);
         st.binom = b;
     }
