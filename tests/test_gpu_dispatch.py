@@ -45,6 +45,8 @@ def test_default_dispatch_matches_the_oracle(default_run):
 @pytest.mark.parametrize("env", [
     {"BP_K3_WARP_MAX_K": 0},                          # 128-thread blocks everywhere
     {"BP_K3_WARP_MAX_K": 8},
+    {"BP_K3_WARP2_MIN_K": 99},                        # one lane per term stream in every one-warp block
+    {"BP_K3_WARP2_MIN_K": 11},
     {"BP_K3_TPG": 2},                                 # up to hundreds of chunk blocks per sample
     {"BP_K3_TPG": 3, "BP_K3_WARP_MAX_K": 0, "BP_K3_CAP": 4},
     {"BP_K3_TREE_MAX_C": 8},                          # two lanes per term stream from k = 9

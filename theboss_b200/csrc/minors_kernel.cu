@@ -605,21 +605,26 @@ struct K3Variant { k3_fn fn; int lpg, c, threads; };
 #define K3_WARP_MAX_C 16
 static K3Variant g_k3[3][K3_MAX_C1 + 1];     // [log2 LPG][C], 128-thread blocks
 static K3Variant g_k3w[K3_WARP_MAX_C + 1];   // LPG = 1, one-warp blocks
+static K3Variant g_k3w2[K3_WARP_MAX_C / 2 + 1];   // LPG = 2, one-warp blocks (k <= 16): [C]
 
 template <int C>
 static void k3_reg() {
     g_k3[0][C] = K3Variant{k3_minors_kernel<1, C, GW_THREADS>, 1, C, GW_THREADS};
     if constexpr (C <= K3_WARP_MAX_C) g_k3w[C] = K3Variant{k3_minors_kernel<1, C, K3_WARP_THREADS>, 1, C, K3_WARP_THREADS};
+    if constexpr (C <= K3_WARP_MAX_C / 2 && C >= 4) g_k3w2[C] = K3Variant{k3_minors_kernel<2, C, K3_WARP_THREADS>, 2, C, K3_WARP_THREADS};
     if constexpr (C <= K3_MAX_C2 && C >= 4) g_k3[1][C] = K3Variant{k3_minors_kernel<2, C, GW_THREADS>, 2, C, GW_THREADS};
     if constexpr (C <= K3_MAX_C4 && C >= 4) g_k3[2][C] = K3Variant{k3_minors_kernel<4, C, GW_THREADS>, 4, C, GW_THREADS};
     if constexpr (C > 1) k3_reg<C - 1>();
 }
 
 // Variant for k input columns: one lane per term stream with all k <= 17 columns, two lanes with ceil(k / 2) columns each for
-// k = 18 .. 30, four lanes for k = 31 .. 48; one-warp blocks for the steps k <= K3_WARP_DEFAULT_MAX_K whose walk fits one block.
-// Tuning knobs, read once: BP_K3_WARP_MAX_K (0 = never one-warp blocks), BP_K3_TREE_MAX_C (column limit per lane, >= 6).
+// k = 18 .. 30, four lanes for k = 31 .. 48; one-warp blocks for the steps k <= K3_WARP_DEFAULT_MAX_K whose walk fits one block --
+// with two lanes per term stream from k = 8 (half the registers per lane, twice the resident blocks: these steps are setup- and
+// latency-bound; n = 16 run -5 %, n = 12 run -8 %, profiles/r02_k3_history.txt).
+// Tuning knobs, read once: BP_K3_WARP_MAX_K (0 = never one-warp blocks), BP_K3_WARP2_MIN_K (first k of the two-lane one-warp blocks),
+// BP_K3_TREE_MAX_C (column limit per lane, >= 6).
 static K3Variant k3_pick(int k) {
-    static int warp_max_k = K3_WARP_DEFAULT_MAX_K, max_c1 = K3_MAX_C1;
+    static int warp_max_k = K3_WARP_DEFAULT_MAX_K, max_c1 = K3_MAX_C1, warp2_min_k = 8;
     static const bool ready = [] {   // thread-safe one-time registration (C++11 static initialisation)
 #ifdef K3_DEV_C   // development builds: a single instantiation (seconds to compile; for SASS inspection only)
         g_k3[0][K3_DEV_C] = K3Variant{k3_minors_kernel<K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS>, K3_DEV_LPG, K3_DEV_C, K3_DEV_THREADS};
@@ -629,6 +634,7 @@ static K3Variant k3_pick(int k) {
         const char *e;
         if ((e = getenv("BP_K3_WARP_MAX_K"))) warp_max_k = atoi(e);
         if ((e = getenv("BP_K3_TREE_MAX_C"))) max_c1 = atoi(e);
+        if ((e = getenv("BP_K3_WARP2_MIN_K"))) warp2_min_k = atoi(e);   // one-warp blocks with two lanes per term stream from this k
         if (max_c1 > K3_MAX_C1) max_c1 = K3_MAX_C1;
         if (max_c1 < 6) max_c1 = 6;
         return true;
@@ -636,6 +642,7 @@ static K3Variant k3_pick(int k) {
     (void)ready;
     K3Variant none = {nullptr, 0, 0, 0};
     if (k < 1) return none;
+    if (k >= warp2_min_k && k <= warp_max_k && k <= K3_WARP_MAX_C && (k + 1) / 2 >= 4 && g_k3w2[(k + 1) / 2].fn) return g_k3w2[(k + 1) / 2];
     // fewest lanes per group whose column count fits the lane limit
     for (int lg = 0; lg < 3; ++lg) {
         const int lpg = 1 << lg, c = (k + lpg - 1) / lpg;
