@@ -272,7 +272,6 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
         unsigned x2base = (unsigned)__cvta_generic_to_shared(X2);
         asm volatile("" : "+r"(x2base));
         double wr = 0.0, wi = 0.0;
-        unsigned cnt = 0;
 
 #pragma unroll 1
         for (unsigned per = 0;;) {
@@ -284,16 +283,14 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
                 const cplx pr = k2_tree<N, 0, N>(sr, si);
                 wr = fma(w, pr.re, wr);
                 wi = fma(w, pr.im, wi);
-                if (++cnt == 64u) {                          // plain accumulation over 64 terms, double-double beyond
-                    cnt = 0;
-                    acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
-                    wr = 0.0; wi = 0.0;
-                }
                 bsgn = -bsgn;
                 blow = e.blow;
                 k2_row_add<N>(x2base + (unsigned)e.off, sr, si);
             }
-            // ---- period boundary: one Guan step of the digits above the table; the table digits stay and reverse
+            // ---- period boundary: the period's plain FP64 sum (P <= 512 terms) goes into the double-double accumulator; then
+            // one Guan step of the digits above the table; the table digits stay and reverse
+            acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+            wr = 0.0; wi = 0.0;
             if (++per >= my_periods) break;
             pos -= pdir;
             pdir = -pdir;
@@ -304,8 +301,6 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
             k2_row_add<N>(x2base + (unsigned)((v + (delta > 0 ? D : 0)) * ROWBYTES), sr, si);
             bsgn = (bsgn < 0.0) ? -st.binom : st.binom;
         }
-        acc_re = dd_add_d(acc_re, wr);
-        acc_im = dd_add_d(acc_im, wi);
     }
     block_reduce_dd(acc_re, acc_im, red);
     if (threadIdx.x == 0) {

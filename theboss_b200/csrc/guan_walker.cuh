@@ -61,89 +61,6 @@ __device__ inline unsigned long long guan_item_build(GuanItem &it, const unsigne
     return terms;
 }
 
-// The same item built by ONE WARP (all 32 lanes of the calling warp must enter; `occ` may live in global memory): the
-// occupied modes are found 32 at a time with a ballot, the top / inner digits by warp arg-max with the serial version's
-// tie rules (first candidate wins), the term count by a product reduction.  Replaces ~m dependent loads of one thread
-// by ~m/32 rounds of the warp: the per-block setup of the batched kernels is latency, not throughput.
-__device__ inline void guan_item_build_warp(GuanItem &it, const unsigned char *occ, int m, bool inner_first = false) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    int D = 0, n = 0;
-    // key of the "top" candidate: odd multiplicity first, then the larger one, then the EARLIER digit
-    int best_key = -1;
-    for (int base = 0; base < m; base += 32) {
-        const int v = base + lane;
-        const int w = (v < m) ? (int)occ[v] : 0;
-        const unsigned mask = __ballot_sync(0xffffffffu, w > 0);
-        const int d = D + __popc(mask & lt);
-        if (w > 0) {
-            if (d < BP_MAX_N) { it.mode[d] = (short)v; it.mult[d] = (unsigned char)w; }
-            const int key = ((((w & 1) << 8) | w) << 8) | (255 - (d < 255 ? d : 255));
-            best_key = key > best_key ? key : best_key;
-        }
-        D += __popc(mask);
-        n += w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n += __shfl_xor_sync(0xffffffffu, n, o);
-        const int other = __shfl_xor_sync(0xffffffffu, best_key, o);
-        best_key = other > best_key ? other : best_key;
-    }
-    if (lane == 0) { it.D = D; it.n = n; }
-    if (D == 0 || D > BP_MAX_N) { if (lane == 0) it.terms = (D == 0) ? 1ull : 0ull; __syncwarp(); return; }
-    __syncwarp();
-    const int top = 255 - (best_key & 255);
-    // move the top digit to the end (digits top+1 .. D-1 shift down by one); D <= 40: two rounds of the warp
-    short tm = it.mode[top]; unsigned char tw = it.mult[top];
-    short mv[2]; unsigned char wv[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int v = lane + 32 * q;
-        if (v >= top && v + 1 < D) { mv[q] = it.mode[v + 1]; wv[q] = it.mult[v + 1]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int v = lane + 32 * q;
-        if (v >= top && v + 1 < D) { it.mode[v] = mv[q]; it.mult[v] = wv[q]; }
-    }
-    if (lane == 0) { it.mode[D - 1] = tm; it.mult[D - 1] = tw; }
-    __syncwarp();
-    if (inner_first && D > 2) {
-        // digit 0 becomes the inner loop: the largest multiplicity among digits 0 .. D-2 (the first one on ties)
-        int key = -1;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int v = lane + 32 * q;
-            if (v < D - 1) { const int kq = ((int)it.mult[v] << 8) | (255 - v); key = kq > key ? kq : key; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const int other = __shfl_xor_sync(0xffffffffu, key, o); key = other > key ? other : key; }
-        const int best = 255 - (key & 255);
-        if (lane == 0 && best != 0) {
-            const short bm = it.mode[best]; const unsigned char bw = it.mult[best];
-            it.mode[best] = it.mode[0]; it.mult[best] = it.mult[0];
-            it.mode[0] = bm; it.mult[0] = bw;
-        }
-        __syncwarp();
-    }
-    unsigned long long terms = 1ull;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int v = lane + 32 * q;
-        if (v < D) {
-            const unsigned char l = (v == D - 1) ? (unsigned char)(it.mult[v] >> 1) : it.mult[v];
-            it.lim[v] = l;
-            terms *= (unsigned long long)(l + 1);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) terms *= __shfl_xor_sync(0xffffffffu, terms, o);
-    if (lane == 0) it.terms = terms;
-    __syncwarp();
-}
-
 // Term count of the halved walk without building the item (cost model of the scheduler).
 __host__ __device__ inline double guan_terms_of(const unsigned char *occ, int m) {
     double full = 1.0;
