@@ -13,7 +13,9 @@ int bp_effective_matrix_launch(bp_context *h, const double *dU, int m, const int
                                int N, double *dA);
 int bp_fp64_peak_launch(bp_context *h, int iters, double *d_sink);
 int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
-                 long long B, double *d_out, const unsigned char *hS, const unsigned char *hT);
+                 long long B, double *d_out, const unsigned char *hS);
+int bp_k2_small_host(bp_context *h, const double *U, int m, const unsigned char *S, const unsigned char *T, long long B, double *out);
+#define BP_K2_SMALL_MAX 256   // (= K2_HOST_PREP_MAX of guan_kernel.cu)
 
 static char g_global_err[512] = "no error";
 
@@ -364,7 +366,7 @@ int bp_perm_batched_dev(bp_handle h, const double *dU, int m, const uint8_t *dS,
     if (formula < BP_FORMULA_RYSER || formula > BP_FORMULA_GLYNN) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: formula %d", formula);
     if (B < 0) return bp_fail(h, BP_ERR_INVALID, "bp_perm_batched_dev: B=%lld", (long long)B);
     BP_ON_DEVICE(h);
-    return bp_k2_launch(h, dU, m, dS, dT, (long long)B, d_out, nullptr, nullptr);
+    return bp_k2_launch(h, dU, m, dS, dT, (long long)B, d_out, nullptr);
 }
 
 int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const uint8_t *T, int64_t B, int formula,
@@ -381,6 +383,7 @@ int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const
         if (ns > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: item %lld has n=%ld > %d", (long long)b, ns, BP_MAX_N);
     }
     BP_ON_DEVICE(h);
+    if (B <= BP_K2_SMALL_MAX) return bp_k2_small_host(h, U, m, S, T, (long long)B, out);
     const size_t ub = sizeof(double) * 2 * (size_t)m * m, sb = (size_t)B * m, ob = sizeof(double) * 2 * (size_t)B;
     int rc;
     if ((rc = bp_reserve(h, BP_SLOT_AUX, ub))) return rc;
@@ -391,7 +394,7 @@ int bp_perm_batched(bp_handle h, const double *U, int m, const uint8_t *S, const
     unsigned char *dS = (unsigned char *)h->d_buf[BP_SLOT_STATE], *dT = dS + ((sb + 15) / 16) * 16;
     BP_CUDA(h, cudaMemcpyAsync(dS, S, sb, cudaMemcpyHostToDevice, h->stream));
     BP_CUDA(h, cudaMemcpyAsync(dT, T, sb, cudaMemcpyHostToDevice, h->stream));
-    rc = bp_k2_launch(h, (const double *)h->d_buf[BP_SLOT_AUX], m, dS, dT, (long long)B, (double *)h->d_buf[BP_SLOT_OUT], S, T);
+    rc = bp_k2_launch(h, (const double *)h->d_buf[BP_SLOT_AUX], m, dS, dT, (long long)B, (double *)h->d_buf[BP_SLOT_OUT], S);
     if (rc) return rc;
     BP_CUDA(h, cudaMemcpyAsync(out, h->d_buf[BP_SLOT_OUT], ob, cudaMemcpyDeviceToHost, h->stream));
     BP_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -356,79 +356,31 @@ static k2_fn g_k2_fn[BP_MAX_N + 1];
 // prep / scan / scatter launches -- a lone compute_permanent() is one copy in, ONE kernel, one copy out.
 #define K2_HOST_PREP_MAX 256
 
-// dU, dS, dT, d_out are device pointers.  hS / hT: the same occupations in host memory, or NULL (device-pointer entry point).
-// With host occupations the per-n item counts are known without asking the device, so nothing synchronises the stream;
-// without them one small D2H copy (the per-n offsets) does.
-int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
-                 long long B, double *d_out, const unsigned char *hS, const unsigned char *hT) {
-    static const bool ready = [] { k2_entry<BP_MAX_N>(g_k2_fn); return true; }();   // thread-safe one-time registration
-    (void)ready;
-    if (B <= 0) return BP_OK;
-    if (B > 0x7fffffffll) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: B=%lld items exceeds 2^31-1", B);
-    const size_t meta_bytes = sizeof(K2Meta) * (size_t)B, order_bytes = sizeof(int) * (size_t)B;
-    const size_t bins_bytes = sizeof(int) * (K2_NBINS + BP_MAX_N + 2);
-    int rc = bp_reserve(h, BP_SLOT_ITEMS, meta_bytes + order_bytes + bins_bytes + 64);
-    if (rc) return rc;
-    char *base = (char *)h->d_buf[BP_SLOT_ITEMS];
-    K2Meta *meta = (K2Meta *)base;
-    int *order = (int *)(base + ((meta_bytes + 15) / 16) * 16);
-    int *bins = (int *)((char *)order + ((order_bytes + 15) / 16) * 16);
-    int *n_offsets = bins + K2_NBINS;
-    int off[BP_MAX_N + 2];
-    if (hS && hT && B <= K2_HOST_PREP_MAX) {
-        // ---- small batch: everything the prep kernels would compute, on the host
-        const size_t pin_need = ((meta_bytes + 15) / 16) * 16 + order_bytes + 64;
-        if ((rc = bp_reserve_pinned(h, pin_need + 4096))) return rc;
-        // (every entry point ends with a stream synchronisation: the staging buffer is never in flight here)
-        K2Meta *hm = (K2Meta *)h->h_pin;
-        int *ho = (int *)((char *)h->h_pin + ((meta_bytes + 15) / 16) * 16);
-        int counts[BP_MAX_N + 2] = {0};
-        for (long long b = 0; b < B; ++b) {
-            const unsigned char *s = hS + b * m, *t = hT + b * m;
-            int ns = 0;
-            for (int v = 0; v < m; ++v) ns += s[v];
-            const double cs = guan_terms_of(s, m), ct = guan_terms_of(t, m);
-            hm[b].n = ns;                                  // (sum(s) == sum(t) <= BP_MAX_N: checked by the caller)
-            hm[b].walk_outputs = (ct < cs) ? 1 : 0;
-            hm[b].log2cost = (float)log2(ct < cs ? ct : cs);
-            ho[b] = (int)b;
-            counts[ns]++;
-        }
-        std::stable_sort(ho, ho + B, [hm](int x, int y) {
-            return hm[x].n != hm[y].n ? hm[x].n < hm[y].n : hm[x].log2cost > hm[y].log2cost;   // by n, longest first inside
-        });
-        off[0] = 0;
-        for (int n = 0; n <= BP_MAX_N; ++n) off[n + 1] = off[n] + counts[n];
-        BP_CUDA(h, cudaMemcpyAsync(meta, hm, meta_bytes, cudaMemcpyHostToDevice, h->stream));
-        BP_CUDA(h, cudaMemcpyAsync(order, ho, order_bytes, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        BP_CUDA(h, cudaMemsetAsync(bins, 0, bins_bytes, h->stream));
-        const int tb = 256, gb = (int)((B + tb - 1) / tb);
-        k2_prep_kernel<<<gb, tb, 0, h->stream>>>(dS, dT, m, B, meta, bins);
-        BP_CHECK_LAUNCH(h);
-        k2_scan_kernel<<<1, 1024, 0, h->stream>>>(bins, n_offsets);
-        BP_CHECK_LAUNCH(h);
-        k2_scatter_kernel<<<gb, tb, 0, h->stream>>>(meta, B, bins, order, d_out);
-        BP_CHECK_LAUNCH(h);
-        if (hS) {
-            // item counts per particle number from the host copy: no round trip to the device
-            int counts[BP_MAX_N + 2] = {0};
-            for (long long b = 0; b < B; ++b) {
-                int ns = 0;
-                const unsigned char *s = hS + b * m;
-                for (int v = 0; v < m; ++v) ns += s[v];
-                counts[ns]++;
-            }
-            off[0] = 0;
-            for (int n = 0; n <= BP_MAX_N; ++n) off[n + 1] = off[n] + counts[n];
-        } else {
-            if ((rc = bp_reserve_pinned(h, 4096))) return rc;
-            int *h_off = (int *)h->h_pin;
-            BP_CUDA(h, cudaMemcpyAsync(h_off, n_offsets, sizeof(int) * (BP_MAX_N + 2), cudaMemcpyDeviceToHost, h->stream));
-            BP_CUDA(h, cudaStreamSynchronize(h->stream));
-            for (int i = 0; i < BP_MAX_N + 2; ++i) off[i] = h_off[i];
-        }
+// Particle numbers, walk side and cost order of a small batch, on the host: what k2_prep / k2_scan / k2_scatter compute.
+static void k2_host_prep(const unsigned char *hS, const unsigned char *hT, int m, long long B, K2Meta *hm, int *ho, int off[BP_MAX_N + 2]) {
+    int counts[BP_MAX_N + 2] = {0};
+    for (long long b = 0; b < B; ++b) {
+        const unsigned char *s = hS + b * m, *t = hT + b * m;
+        int ns = 0;
+        for (int v = 0; v < m; ++v) ns += s[v];
+        const double cs = guan_terms_of(s, m), ct = guan_terms_of(t, m);
+        hm[b].n = ns;                                  // (sum(s) == sum(t) <= BP_MAX_N: checked by the caller)
+        hm[b].walk_outputs = (ct < cs) ? 1 : 0;
+        hm[b].log2cost = (float)log2(ct < cs ? ct : cs);
+        ho[b] = (int)b;
+        counts[ns]++;
     }
+    std::stable_sort(ho, ho + B, [hm](int x, int y) {
+        return hm[x].n != hm[y].n ? hm[x].n < hm[y].n : hm[x].log2cost > hm[y].log2cost;   // by n, longest first inside
+    });
+    off[0] = 0;
+    for (int n = 0; n <= BP_MAX_N; ++n) off[n + 1] = off[n] + counts[n];
+}
+
+// One templated launch per distinct particle number over the items order[off[n] .. off[n + 1]).
+static int k2_run(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT, const K2Meta *meta,
+                  const int *order, const int off[BP_MAX_N + 2], double *d_out) {
+    int rc;
     for (int n = 0; n <= BP_MAX_N; ++n) {
         const int count = off[n + 1] - off[n];
         if (count <= 0) continue;
@@ -465,4 +417,84 @@ int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS
         }
     }
     return BP_OK;
+}
+
+static void k2_register() {
+    static const bool ready = [] { k2_entry<BP_MAX_N>(g_k2_fn); return true; }();   // thread-safe one-time registration
+    (void)ready;
+}
+
+// Host-pointer batch of at most K2_HOST_PREP_MAX items (a lone compute_permanent() above all): matrix, occupations, item
+// metadata and order travel in ONE staged upload, the results in one download; no prep kernels, no synchronisation but the last.
+int bp_k2_small_host(bp_context *h, const double *U, int m, const unsigned char *S, const unsigned char *T, long long B, double *out) {
+    k2_register();
+    auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t ub = sizeof(double) * 2 * (size_t)m * m, sb = (size_t)B * m;
+    const size_t o_S = ub, o_T = o_S + up16(sb), o_meta = o_T + up16(sb), o_order = o_meta + up16(sizeof(K2Meta) * (size_t)B);
+    const size_t in_bytes = o_order + up16(sizeof(int) * (size_t)B), out_bytes = sizeof(double) * 2 * (size_t)B;
+    int rc;
+    if ((rc = bp_reserve(h, BP_SLOT_ITEMS, in_bytes + out_bytes))) return rc;
+    if ((rc = bp_reserve_pinned(h, in_bytes + out_bytes))) return rc;
+    // (every entry point ends with a stream synchronisation: the staging buffer is never in flight here)
+    char *hp = (char *)h->h_pin, *dp = (char *)h->d_buf[BP_SLOT_ITEMS];
+    memcpy(hp, U, ub);
+    memcpy(hp + o_S, S, sb);
+    memcpy(hp + o_T, T, sb);
+    int off[BP_MAX_N + 2];
+    k2_host_prep(S, T, m, B, (K2Meta *)(hp + o_meta), (int *)(hp + o_order), off);
+    BP_CUDA(h, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    double *d_out = (double *)(dp + in_bytes);
+    if ((rc = k2_run(h, (const double *)dp, m, (const unsigned char *)(dp + o_S), (const unsigned char *)(dp + o_T),
+                     (const K2Meta *)(dp + o_meta), (const int *)(dp + o_order), off, d_out))) return rc;
+    BP_CUDA(h, cudaMemcpyAsync(hp + in_bytes, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(out, hp + in_bytes, out_bytes);
+    return BP_OK;
+}
+
+// dU, dS, dT, d_out are device pointers.  hS: the input occupations in host memory too, or NULL (device-pointer entry point).
+// With the host copy the per-n item counts are known without asking the device, so nothing synchronises the stream;
+// without it one small D2H copy (the per-n offsets) does.
+int bp_k2_launch(bp_context *h, const double *dU, int m, const unsigned char *dS, const unsigned char *dT,
+                 long long B, double *d_out, const unsigned char *hS) {
+    k2_register();
+    if (B <= 0) return BP_OK;
+    if (B > 0x7fffffffll) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_perm_batched: B=%lld items exceeds 2^31-1", B);
+    const size_t meta_bytes = sizeof(K2Meta) * (size_t)B, order_bytes = sizeof(int) * (size_t)B;
+    const size_t bins_bytes = sizeof(int) * (K2_NBINS + BP_MAX_N + 2);
+    int rc = bp_reserve(h, BP_SLOT_ITEMS, meta_bytes + order_bytes + bins_bytes + 64);
+    if (rc) return rc;
+    char *base = (char *)h->d_buf[BP_SLOT_ITEMS];
+    K2Meta *meta = (K2Meta *)base;
+    int *order = (int *)(base + ((meta_bytes + 15) / 16) * 16);
+    int *bins = (int *)((char *)order + ((order_bytes + 15) / 16) * 16);
+    int *n_offsets = bins + K2_NBINS;
+    int off[BP_MAX_N + 2];
+    BP_CUDA(h, cudaMemsetAsync(bins, 0, bins_bytes, h->stream));
+    const int tb = 256, gb = (int)((B + tb - 1) / tb);
+    k2_prep_kernel<<<gb, tb, 0, h->stream>>>(dS, dT, m, B, meta, bins);
+    BP_CHECK_LAUNCH(h);
+    k2_scan_kernel<<<1, 1024, 0, h->stream>>>(bins, n_offsets);
+    BP_CHECK_LAUNCH(h);
+    k2_scatter_kernel<<<gb, tb, 0, h->stream>>>(meta, B, bins, order, d_out);
+    BP_CHECK_LAUNCH(h);
+    if (hS) {
+        // item counts per particle number from the host copy: no round trip to the device
+        int counts[BP_MAX_N + 2] = {0};
+        for (long long b = 0; b < B; ++b) {
+            int ns = 0;
+            const unsigned char *s = hS + b * m;
+            for (int v = 0; v < m; ++v) ns += s[v];
+            counts[ns]++;
+        }
+        off[0] = 0;
+        for (int n = 0; n <= BP_MAX_N; ++n) off[n + 1] = off[n] + counts[n];
+    } else {
+        if ((rc = bp_reserve_pinned(h, 4096))) return rc;
+        int *h_off = (int *)h->h_pin;
+        BP_CUDA(h, cudaMemcpyAsync(h_off, n_offsets, sizeof(int) * (BP_MAX_N + 2), cudaMemcpyDeviceToHost, h->stream));
+        BP_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < BP_MAX_N + 2; ++i) off[i] = h_off[i];
+    }
+    return k2_run(h, dU, m, dS, dT, meta, order, off, d_out);
 }
