@@ -422,7 +422,6 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
     __shared__ double2 P[BP_MAX_MODES];
     __shared__ double wgt[BP_MAX_MODES];
-    __shared__ short first_col[BP_MAX_MODES];
     __shared__ double total_sh;
     __shared__ int idx_sh;
     // chunk reduction of the few samples that had the whole GPU (up to 296 chunk blocks each): K3F_PARTS interleaved slices
@@ -444,7 +443,7 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
     if (threadIdx.x == 0) idx_sh = 0;
     __syncthreads();
     if (threadIdx.x < 32) {
-        // first column of every occupied input mode and the list of occupied modes: warp scan over 32 modes at a time
+        // the list of occupied input modes with the first column of each: warp scan over 32 modes at a time
         // (low half: particles = columns before the mode, high half: occupied modes before it)
         const int lane = threadIdx.x;
         int carry_c = 0, carry_o = 0;
@@ -458,7 +457,6 @@ __global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
                 if (lane >= d) x += y;
             }
             const int c = carry_c + (x & 0xffff) - sv, o = carry_o + (x >> 16) - occ;
-            if (v < m) first_col[v] = occ ? (short)c : (short)-1;
             if (occ && o < BP_MAX_N + 2) { occ_mode[o] = (short)v; occ_col[o] = (short)c; }
             const int tot = __shfl_sync(0xffffffffu, x, 31);
             carry_c += tot & 0xffff;
