@@ -1,5 +1,5 @@
 """A/B timing of the GCC-B sampling loop under the K3 dispatch knobs read from the environment
-(BP_K3_WARP_MAX_K, BP_K3_WIDE_MIN_K, BP_K3_TPG, ...).  One process per setting (the knobs are read once);
+(BP_K3_WARP_MAX_K, BP_K3_WARP2_MIN_K, BP_K3_TREE_MAX_C, BP_K3_TPG, BP_K3_CAP).  One process per setting (the knobs are read once);
 prints the best of `reps` wall-clock runs per workload plus a checksum of the samples (all settings must agree)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

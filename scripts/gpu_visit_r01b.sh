@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: this visit ran on an earlier build; some BP_K3_* knobs it sets (ENGINE, WIDE_MIN_K, MAX_C) were removed with the engines they selected.
 # GPU visit for the one-warp K3 blocks: tests, smoke, A/B timings of the dispatch knobs, sanitizer, bench, launch list.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1

@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: this visit ran on an earlier build; some BP_K3_* knobs it sets (ENGINE, WIDE_MIN_K, MAX_C) were removed with the engines they selected.
 # GPU visit: A/B of K3 block shapes for the large steps (256-thread blocks, 3 blocks/SM for C = 9, 10).
 mkdir -p gpurun_out
 L=theboss_b200/lib

@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: this visit ran on an earlier build; some BP_K3_* knobs it sets (ENGINE, WIDE_MIN_K, MAX_C) were removed with the engines they selected.
 # Round 2, visit 1: parity of the tree engine (K3) + A/B against the scan engine + per-step FP64 pipe + flop cross-check.
 #   gpurun --timeout 1200 -- 'bash scripts/gpu_visit_r02b.sh'
 set -x

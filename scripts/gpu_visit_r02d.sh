@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: this visit ran on an earlier build; some BP_K3_* knobs it sets (ENGINE, WIDE_MIN_K, MAX_C) were removed with the engines they selected.
 # Round 2, visit 3: engine 2 of K3 (one uniform term loop): parity under BP_K3_ENGINE=2, A/B against engine 1, per-step pipe.
 #   gpurun --timeout 1200 -- 'bash scripts/gpu_visit_r02d.sh'
 set -x

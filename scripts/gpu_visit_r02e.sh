@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: this visit ran on an earlier build; some BP_K3_* knobs it sets (ENGINE, WIDE_MIN_K, MAX_C) were removed with the engines they selected.
 # Round 2, visit 4: engine 2 with three blocks per SM up to C = 12 (lib variant u3) against the plain engine 2 build.
 set -x
 mkdir -p gpurun_out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# HISTORICAL: this visit ran on an earlier build; some BP_K3_* knobs it sets (ENGINE, WIDE_MIN_K, MAX_C) were removed with the engines they selected.
 # Times GCC-B sampling runs under different K3 work-sizing knobs (BP_K3_TPG = terms per lane group and block,
 # BP_K3_CAP = chunk blocks per sample when samples are plentiful).
 mkdir -p gpurun_out
