@@ -82,3 +82,32 @@ def test_c5_lossy_runs_conserve_particles(handle):
     assert np.all(out.sum(axis=1) == n_small)                                         # every particle lands somewhere in 2m modes
     survived = out[:, :60].sum(axis=1).mean() / n_small
     assert abs(survived - np.linspace(0.3, 0.9, 60)[:n_small].mean()) < 0.08          # mean transmissivity of the used inputs
+
+
+def test_c5_nonuniform_losses_at_full_size_through_the_strategy(handle):
+    """BASELINE config 5(ii) as quoted: n = 30 photons, m = 60, non-uniform losses, through
+    LossyNetworksGeneralizedCliffordsSimulationStrategy (lossy_networks_generalized_cliffords_simulation_strategy.py:41-88) -- i.e.
+    GCC-B on the 120-mode dilation, steps k = 18 .. 30 in the two-lane kernels.  Size-independent properties: every particle is
+    either detected or sits in a loss mode, a loss mode never holds more particles than the single input it couples to sent in,
+    the detected fraction follows the transmissivities, and the samples do not depend on how the request is split."""
+    from theboss_b200.boson_sampling_utilities.boson_sampling_utilities import prepare_interferometer_matrix_in_expanded_space
+    from theboss_b200.boson_sampling_utilities.permanent_calculators.ryser_permanent_calculator import RyserPermanentCalculator
+    from theboss_b200.simulation_strategies.lossy_networks_generalized_cliffords_simulation_strategy import (
+        LossyNetworksGeneralizedCliffordsSimulationStrategy)
+    U, U_lossy, s = workloads.c5_lossy(30, 60)
+    big = np.ascontiguousarray(prepare_interferometer_matrix_in_expanded_space(U_lossy))
+    s_big = np.concatenate([s, np.zeros(60, dtype=np.int32)])
+    full = handle.gccb_simulate(big, s_big, 24, seed=62)
+    assert np.all(full.sum(axis=1) == 30)
+    loss_mode_of_input = [60 + int(np.argmax(np.abs(big[60:, i]))) for i in range(30)]
+    assert len(set(loss_mode_of_input)) == 30
+    lost = full[:, 60:]
+    assert lost.max() <= 1 and np.all(lost[:, [j - 60 for j in range(60, 120) if j not in loss_mode_of_input]] == 0)
+    detected = full[:, :60].sum(axis=1).mean() / 30
+    assert abs(detected - np.linspace(0.3, 0.9, 60)[:30].mean()) < 0.12
+    parts = [handle.gccb_simulate(big, s_big, 8, seed=62, first_sample=lo) for lo in (0, 8, 16)]
+    assert np.array_equal(np.concatenate(parts), full)
+    strategy = LossyNetworksGeneralizedCliffordsSimulationStrategy(RyserPermanentCalculator(U_lossy))
+    np.random.seed(5)
+    samples = strategy.simulate([int(x) for x in s], 6)
+    assert len(samples) == 6 and all(len(x) == 60 and 0 <= sum(x) <= 30 for x in samples)
