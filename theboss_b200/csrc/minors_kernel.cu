@@ -419,21 +419,27 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
 // ---------------------------------------------------------------------------------------------
 #define K3F_THREADS 64
 #define K3F_PARTS 16
-__global__ void __launch_bounds__(512) k3_finish_kernel(K3Finish a) {
-    __shared__ double2 P[BP_MAX_MODES];
-    __shared__ double wgt[BP_MAX_MODES];
+// dynamic shared memory of the finish kernel: psum[(BP_MAX_N + 2) * parts * 4] doubles, P[m] double2, wgt[m] doubles, s_sh[m] bytes --
+// sized by m (not BP_MAX_MODES) and 32 registers per thread, so that the 64-thread blocks of a 4096-sample batch (27.7 per SM) are
+// all resident at once: one wave instead of two (24 blocks per SM before; profiles/r02_finish_ncu_summary.txt)
+static inline size_t k3_finish_smem(int m, int parts) {
+    return sizeof(double) * 4 * (BP_MAX_N + 2) * (size_t)parts + (sizeof(double2) + sizeof(double)) * (size_t)m + ((size_t)m + 15) / 16 * 16;
+}
+__global__ void __launch_bounds__(512, 4) k3_finish_kernel(K3Finish a, int parts_alloc) {
+    extern __shared__ __align__(16) double psum[];   // [(BP_MAX_N + 2) * parts_alloc * 4]: parts_alloc = K3F_PARTS when chunks > 32, else 1
+    double2 *P = reinterpret_cast<double2 *>(psum + 4 * (BP_MAX_N + 2) * parts_alloc);        // [m]
+    double *wgt = reinterpret_cast<double *>(P + a.m);                                       // [m]
+    unsigned char *s_sh = reinterpret_cast<unsigned char *>(wgt + a.m);                      // [m] input occupation of this sample
     __shared__ double total_sh;
     __shared__ int idx_sh;
     // chunk reduction of the few samples that had the whole GPU (up to 296 chunk blocks each): K3F_PARTS interleaved slices
     // per column summed by different threads, then added in slice order (fixed order); batches (<= 32 chunks) use one slice
     __shared__ short occ_mode[BP_MAX_N + 2], occ_col[BP_MAX_N + 2];
     __shared__ int nocc_sh;
-    extern __shared__ double psum[];   // [(BP_MAX_N + 2) * parts * 4]: parts = K3F_PARTS when chunks > 32, else 1 (host sizes it)
     const int slot = blockIdx.x, m = a.m, k = a.step + 1;
     const int sample = a.order ? a.order[slot] : slot;
     if (a.steps_total && a.step >= a.steps_total[sample]) return;
     unsigned char *s = a.occ_s + (size_t)sample * m, *t = a.occ_t + (size_t)sample * m;
-    __shared__ unsigned char s_sh[BP_MAX_MODES];               // input occupation of this sample
     __shared__ double sp_re[BP_MAX_N + 2], sp_im[BP_MAX_N + 2];  // s_i * P_i of the occupied input modes, mode order
     for (int v = threadIdx.x; v < m; v += blockDim.x) {
         const unsigned char sv = s[v];
@@ -729,8 +735,8 @@ int bp_k3_finish_launch(bp_context *h, const K3Finish &a, long long samples) {
     // few samples (< 2 x SM count) may have up to 2 x SM-count chunk partials per column to add: give their blocks more threads
     const bool many_chunks = a.chunks > 32;
     const int threads = many_chunks ? 512 : K3F_THREADS;
-    const size_t smem = sizeof(double) * 4 * (BP_MAX_N + 2) * (many_chunks ? K3F_PARTS : 1);
-    k3_finish_kernel<<<(unsigned)samples, threads, smem, h->stream>>>(a);
+    const int parts = many_chunks ? K3F_PARTS : 1;
+    k3_finish_kernel<<<(unsigned)samples, threads, k3_finish_smem(a.m, parts), h->stream>>>(a, parts);
     BP_CHECK_LAUNCH(h);
     return BP_OK;
 }
