@@ -161,13 +161,8 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
     const K2Meta me = meta[b];   // (blockIdx.y = chunk of this item's walk)
     const unsigned char *walk = (me.walk_outputs ? T : S) + (long long)b * m;
     const unsigned char *prod = (me.walk_outputs ? S : T) + (long long)b * m;
-    if (threadIdx.x == 0) {
-        guan_item_build(item, walk, m, /*inner_first=*/true);
-    } else if (threadIdx.x == 32) {
-        int c = 0;
-        for (int v = 0; v < m; ++v)
-            for (int a = 0; a < prod[v] && c < N; ++a) col_mode[c++] = (short)v;
-    }
+    if (threadIdx.x < 32) guan_item_build_warp(item, walk, m, /*inner_first=*/true);       // block setup by whole warps
+    else if (threadIdx.x < 64) guan_expand_columns_warp(col_mode, prod, m, N);
     __syncthreads();
     const int D = item.D;
     double2 *X2 = reinterpret_cast<double2 *>(k2_smem);             // rows [0, D): +2X, [D, 2D): -2X, row 2D: 0

@@ -23,42 +23,113 @@ struct GuanItem {                 // block-uniform description of one walk, live
     short mode[BP_MAX_N];         // mode index of digit v
 };
 
-// Orders the digits of an occupation vector: all occupied modes in mode order, except that the
-// digit chosen as "top" (an odd multiplicity if there is one, else the largest) is moved last.
-// Single-thread helper (called by thread 0 of a block).  Returns the halved term count.
-__device__ inline unsigned long long guan_item_build(GuanItem &it, const unsigned char *occ, int m, bool inner_first = false) {
-    int D = 0, n = 0, top = -1, top_w = 0;
-    for (int v = 0; v < m; ++v) {
-        const int w = occ[v];
-        if (!w) continue;
+// Orders the digits of an occupation vector: all occupied modes in mode order, except that the digit chosen as "top" (an odd
+// multiplicity if there is one, else the largest; the first candidate wins ties) is moved last and -- inner_first -- the largest
+// multiplicity among the others becomes digit 0 (the fastest digit of the step tables).  Built by ONE WARP (all 32 lanes of
+// the calling warp must enter; `occ` may live in global memory): the occupied modes are found 32 at a time with a ballot, the
+// top / inner digits by warp arg-max, the halved term count by a product reduction -- ~m/32 rounds of the warp where one thread
+// looping over m modes was half of the instructions of a small sampling step.
+__device__ inline void guan_item_build_warp(GuanItem &it, const unsigned char *occ, int m, bool inner_first = false) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int D = 0, n = 0;
+    // key of the "top" candidate: odd multiplicity first, then the larger one, then the EARLIER digit
+    int best_key = -1;
+    for (int base = 0; base < m; base += 32) {
+        const int v = base + lane;
+        const int w = (v < m) ? (int)occ[v] : 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, w > 0);
+        const int d = D + __popc(mask & lt);
+        if (w > 0) {
+            if (d < BP_MAX_N) { it.mode[d] = (short)v; it.mult[d] = (unsigned char)w; }
+            const int key = ((((w & 1) << 8) | w) << 8) | (255 - (d < 255 ? d : 255));
+            best_key = key > best_key ? key : best_key;
+        }
+        D += __popc(mask);
         n += w;
-        const bool better = (top < 0) || ((w & 1) && !(top_w & 1)) || (((w & 1) == (top_w & 1)) && w > top_w);
-        if (better) { top = D; top_w = w; }
-        if (D < BP_MAX_N) { it.mode[D] = (short)v; it.mult[D] = (unsigned char)w; }
-        ++D;
     }
-    it.D = D; it.n = n;
-    if (D == 0 || D > BP_MAX_N) { it.terms = (D == 0) ? 1ull : 0ull; return it.terms; }
-    // move the top digit to the end
-    const short tm = it.mode[top];
-    const unsigned char tw = it.mult[top];
-    for (int v = top; v + 1 < D; ++v) { it.mode[v] = it.mode[v + 1]; it.mult[v] = it.mult[v + 1]; }
-    it.mode[D - 1] = tm; it.mult[D - 1] = tw;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        const int other = __shfl_xor_sync(0xffffffffu, best_key, o);
+        best_key = other > best_key ? other : best_key;
+    }
+    if (lane == 0) { it.D = D; it.n = n; }
+    if (D == 0 || D > BP_MAX_N) { if (lane == 0) it.terms = (D == 0) ? 1ull : 0ull; __syncwarp(); return; }
+    __syncwarp();
+    const int top = 255 - (best_key & 255);
+    // move the top digit to the end (digits top+1 .. D-1 shift down by one); D <= 40: two rounds of the warp
+    short tm = it.mode[top]; unsigned char tw = it.mult[top];
+    short mv[2]; unsigned char wv[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int v = lane + 32 * q;
+        if (v >= top && v + 1 < D) { mv[q] = it.mode[v + 1]; wv[q] = it.mult[v + 1]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int v = lane + 32 * q;
+        if (v >= top && v + 1 < D) { it.mode[v] = mv[q]; it.mult[v] = wv[q]; }
+    }
+    if (lane == 0) { it.mode[D - 1] = tm; it.mult[D - 1] = tw; }
+    __syncwarp();
     if (inner_first && D > 2) {
-        // digit 0 becomes the inner loop of the minors kernel: give it the largest multiplicity
-        int best = 0;
-        for (int v = 1; v < D - 1; ++v) if (it.mult[v] > it.mult[best]) best = v;
-        const short bm = it.mode[best]; const unsigned char bw = it.mult[best];
-        it.mode[best] = it.mode[0]; it.mult[best] = it.mult[0];
-        it.mode[0] = bm; it.mult[0] = bw;
+        // digit 0 becomes the inner loop: the largest multiplicity among digits 0 .. D-2 (the first one on ties)
+        int key = -1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int v = lane + 32 * q;
+            if (v < D - 1) { const int kq = ((int)it.mult[v] << 8) | (255 - v); key = kq > key ? kq : key; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int other = __shfl_xor_sync(0xffffffffu, key, o); key = other > key ? other : key; }
+        const int best = 255 - (key & 255);
+        if (lane == 0 && best != 0) {
+            const short bm = it.mode[best]; const unsigned char bw = it.mult[best];
+            it.mode[best] = it.mode[0]; it.mult[best] = it.mult[0];
+            it.mode[0] = bm; it.mult[0] = bw;
+        }
+        __syncwarp();
     }
-    unsigned long long terms = 1;
-    for (int v = 0; v < D; ++v) {
-        it.lim[v] = (v == D - 1) ? (unsigned char)(it.mult[v] >> 1) : it.mult[v];
-        terms *= (unsigned long long)(it.lim[v] + 1);
+    unsigned long long terms = 1ull;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int v = lane + 32 * q;
+        if (v < D) {
+            const unsigned char l = (v == D - 1) ? (unsigned char)(it.mult[v] >> 1) : it.mult[v];
+            it.lim[v] = l;
+            terms *= (unsigned long long)(l + 1);
+        }
     }
-    it.terms = terms;
-    return terms;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) terms *= __shfl_xor_sync(0xffffffffu, terms, o);
+    if (lane == 0) it.terms = terms;
+    __syncwarp();
+}
+
+
+// Expands an occupation vector into its particle list by ONE WARP: col_mode[c] = mode of particle c (mode order), entries beyond
+// the particles up to `width` are -1.  32 modes per round, positions from a warp scan.
+__device__ inline void guan_expand_columns_warp(short *col_mode, const unsigned char *occ, int m, int width) {
+    const int lane = threadIdx.x & 31;
+    int carry = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int v = base + lane;
+        const int w = (v < m) ? (int)occ[v] : 0;
+        int x = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        const int start = carry + x - w;
+        for (int a = 0; a < w; ++a)
+            if (start + a < width) col_mode[start + a] = (short)v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    for (int c = carry + lane; c < width; c += 32) col_mode[c] = -1;
+    __syncwarp();
 }
 
 // Term count of the halved walk without building the item (cost model of the scheduler).

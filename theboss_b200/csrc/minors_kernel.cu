@@ -187,13 +187,13 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     if (steps_total && step >= steps_total[sample]) return;   // uniform-loss variant: this sample is complete
 
     const unsigned char *s = occ_s + (size_t)sample * m, *t = occ_t + (size_t)sample * m;
-    if (threadIdx.x == 0) {
-        guan_item_build(item, t, m, /*inner_first=*/true);
-    } else if (threadIdx.x == (THREADS > 32 ? 32 : 1)) {   // a second warp (lane, in one-warp blocks) expands the input columns meanwhile
-        int c = 0;
-        for (int v = 0; v < m; ++v)
-            for (int a = 0; a < s[v] && c < W; ++a) col_mode[c++] = (short)v;
-        for (; c < W; ++c) col_mode[c] = -1;
+    // block setup by whole warps (ballots and scans over 32 modes at a time instead of one thread looping over m modes: the
+    // serial version was half of the instructions of a small step, profiles/r02_k3_small_step_ncu.txt)
+    if (threadIdx.x < 32) {
+        guan_item_build_warp(item, t, m, /*inner_first=*/true);
+        if (THREADS == 32) guan_expand_columns_warp(col_mode, s, m, W);
+    } else if (threadIdx.x < 64) {                          // a second warp expands the input columns meanwhile
+        guan_expand_columns_warp(col_mode, s, m, W);
     }
     __syncthreads();
     const int D = item.D;
