@@ -199,8 +199,7 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
         int chg = 0, up = 0;
         for (int v = 0; v <= a_low; ++v) {
             const unsigned R = (unsigned)item.lim[v] + 1u;
-            unsigned d = q % R; q /= R;
-            unsigned dm = qm % R; qm /= R;
+            const unsigned d = gw_divmod(q, R), dm = gw_divmod(qm, R);
             const int rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
             const int rm = (qm & 1u) ? (int)item.lim[v] - (int)dm : (int)dm;
             if (p && rv != rm) { chg = v; up = rv > rm; }
@@ -246,7 +245,7 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
                 int rv;
                 if (v <= a_low) {
                     const unsigned R = (unsigned)item.lim[v] + 1u;
-                    const unsigned d = q % R; q /= R;
+                    const unsigned d = gw_divmod(q, R);
                     rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
                 } else rv = (int)r[v * GW_THREADS];
                 par += rv;

@@ -154,6 +154,16 @@ static __constant__ double gw_rcp[BP_MAX_N + 2] = {
     1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27,
     1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41};
 
+// d = q mod R, q = q div R for a digit radix R = lim + 1 (block-uniform).  Collision-free digits (R = 2, the usual case) and
+// single-valued ones (R = 1) take no division: the position decodes of the block setup were mostly 32-bit divisions.
+__device__ __forceinline__ unsigned gw_divmod(unsigned &q, unsigned R) {
+    unsigned d;
+    if (R == 2u)      { d = q & 1u; q >>= 1; }
+    else if (R == 1u) { d = 0u; }
+    else              { d = q % R; q /= R; }
+    return d;
+}
+
 struct GuanState {                // per-thread
     unsigned long long dirmask;   // bit v set: digit v currently moves downwards
     double binom;                 // prod_v C(w_v, r_v) * (top weight 1 or 2), exact integer
@@ -183,7 +193,7 @@ __device__ inline void guan_seek(const GuanItem &it, unsigned long long I, unsig
         const unsigned R = (unsigned)it.lim[v] + 1u;
         unsigned d;
         if (q >> 32) { d = (unsigned)(q % R); q /= R; }                                   // 64-bit division: ~10x the cost, rare
-        else         { const unsigned q32 = (unsigned)q; d = q32 % R; q = q32 / R; }
+        else         { unsigned q32 = (unsigned)q; d = gw_divmod(q32, R); q = q32; }
         int rv;
         if (q & 1ull) { rv = (int)it.lim[v] - (int)d; st.dirmask |= (1ull << v); }
         else          { rv = (int)d; }

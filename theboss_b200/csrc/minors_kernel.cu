@@ -239,8 +239,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         int chg = 0, up = 0;
         for (int v = 0; v <= a_low; ++v) {
             const unsigned R = (unsigned)item.lim[v] + 1u;
-            unsigned d = q % R; q /= R;
-            unsigned dm = qm % R; qm /= R;
+            const unsigned d = gw_divmod(q, R), dm = gw_divmod(qm, R);
             const int rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
             const int rm = (qm & 1u) ? (int)item.lim[v] - (int)dm : (int)dm;
             if (p && rv != rm) { chg = v; up = rv > rm; }
@@ -298,7 +297,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
                 int rv;
                 if (v <= a_low) {
                     const unsigned R = (unsigned)item.lim[v] + 1u;
-                    const unsigned d = q % R; q /= R;
+                    const unsigned d = gw_divmod(q, R);
                     rv = (q & 1u) ? (int)item.lim[v] - (int)d : (int)d;
                 } else rv = (int)r[v * THREADS];
                 par += rv;
