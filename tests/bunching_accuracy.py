@@ -1,7 +1,7 @@
 """Relative error of K2 / K3 under heavy bunching (the cases of tests/test_gpu_edges.py) against the 80-bit oracle, next to the error
 of the double-precision restatement of the reference (which uses pow() for repeated factors)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import numpy as np
 from tests import workloads
 from theboss_b200 import _native

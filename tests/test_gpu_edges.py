@@ -43,7 +43,7 @@ def test_heavy_bunching_up_to_forty_particles(handle, orc):
     """n = 40 (BP_MAX_N) concentrated in a few modes: tiny walks, large binomial weights.  With 20-fold
     bunching the Chin-Huh sum cancels ~10 digits in ANY float64 evaluation (the reference's included), so
     the bar is 1e-10 or 12x the error of the double-precision restatement of the reference, whichever is
-    looser (measured, scripts/bunching_accuracy.py: kernel 8e-10 / 1e-9 / 1.5e-11 / 9e-11 against 9e-11 / 9e-10 / 1.3e-12 / 6e-11
+    looser (measured, tests/bunching_accuracy.py: kernel 8e-10 / 1e-9 / 1.5e-11 / 9e-11 against 9e-11 / 9e-10 / 1.3e-12 / 6e-11
     of the reference's arithmetic; round 1, before the product tree: up to 2e-9)."""
     m = 8
     U = workloads.haar(m, 40)
