@@ -97,6 +97,9 @@ __global__ void k2_scatter_kernel(const K2Meta *__restrict__ meta, long long B, 
 // main kernel
 // ---------------------------------------------------------------------------------------------
 #define K2_PMAX 512
+#ifndef K2_PERIODS_PER_THREAD
+#define K2_PERIODS_PER_THREAD 8    // a thread owns at least this many periods (thread ranges differ by at most one period; 16 -> 8: config 2 -1.1 %)
+#endif
 struct __align__(16) K2Step { double blow; int off; int pad; };   // binomial product at the position; byte offset of the signed row that leads there
 
 // 16-byte shared-memory load at a 32-bit shared-window address plus a compile-time byte offset (one address register per row)
@@ -184,7 +187,7 @@ k2_perm_kernel(const double *__restrict__ U, int m, const unsigned char *__restr
         int a = -1;
         for (int v = 0; v < D; ++v) {
             const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
-            if (v > 0 && (nxt * 16 > raw || nxt > K2_PMAX)) break;   // digit 0 always: work is dealt out in whole sweeps of it
+            if (v > 0 && (nxt * K2_PERIODS_PER_THREAD > raw || nxt > K2_PMAX)) break;   // digit 0 always: work is dealt out in whole sweeps of it
             P = nxt; a = v;
         }
         period = (unsigned)P;

@@ -117,6 +117,9 @@ __device__ __forceinline__ void k3_tree_down_real(double w, const double (&cr)[C
 // walk by orders of magnitude, so the grid is sized for the collision-free worst case and blocks beyond
 // `active` exit at once; the finish kernel applies the same rule.
 #define K3_TERMS_PER_GROUP 192ull
+#ifndef K3_PERIODS_PER_GROUP
+#define K3_PERIODS_PER_GROUP 8    // a lane group owns at least this many table periods (group ranges differ by at most one period; 16 -> 8: n = 24 run -0.5 %, n = 16 run -3 %)
+#endif
 #define K3_PMAX 512
 // One-warp blocks (THREADS = 32) serve the steps k <= 16, where a sample's whole walk fits one block and the
 // per-block setup (item build, tables, seek: largely single-thread work) dominates: with 4x more, 4x smaller
@@ -232,7 +235,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
         int a = -1;
         for (int v = 0; v < D; ++v) {
             const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
-            if (v > 0 && (nxt * 16 > raw || nxt > (unsigned long long)PMAX)) break;
+            if (v > 0 && (nxt * K3_PERIODS_PER_GROUP > raw || nxt > (unsigned long long)PMAX)) break;
             P = nxt; a = v;
         }
         period = (unsigned)P;
