@@ -230,7 +230,7 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
     const unsigned long long ngroups = (unsigned long long)active * GROUPS;
     if (threadIdx.x == 0) {
         // table digits: digit 0 always (work is dealt out in whole sweeps of it), further digits while a lane group still
-        // gets ~16 periods (balance: group ranges differ by at most one period) and the table fits
+        // gets K3_PERIODS_PER_GROUP periods (balance: group ranges differ by at most one period) and the table fits
         unsigned long long raw = (terms + ngroups - 1) / ngroups, P = 1;
         int a = -1;
         for (int v = 0; v < D; ++v) {
