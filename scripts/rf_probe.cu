@@ -9,10 +9,26 @@
 //   5  a = fma(b_i, c_j, a) in PAIRS that share b_i (complex-multiply pattern: re/im of one product share one factor)
 //   7  like 0 with an integer add after every second DFMA (does the reuse cache survive an instruction of another pipe?)
 //   8  like 1 with 8 accumulators
+//   9  like 4, and every fourth DADD is followed by a 16-byte shared-memory load (same address in all lanes) that refills two b's
+//  10  like 9 with a different address per lane (conflict-free, four wavefronts per load)
+//  11  like 9 with an 8-byte load (one b) after every second DADD
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+template <int MODE, int Q>
+__device__ __forceinline__ void lds_body(double (&a)[16], double (&b)[16], unsigned saddr) {
+    if constexpr (Q < 64) {
+        constexpr int i = Q & 15, j = (Q * 5 + 3) & 15;
+        asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(a[i]) : "d"(b[j]));
+        if constexpr (MODE != 11 && (Q & 3) == 3)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(b[(Q >> 1) & 14]), "=d"(b[((Q >> 1) & 14) + 1]) : "r"(saddr), "n"((Q >> 2) * 16));
+        if constexpr (MODE == 11 && (Q & 1) == 1)
+            asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(b[(Q >> 1) & 15]) : "r"(saddr), "n"((Q >> 1) * 8));
+        lds_body<MODE, Q + 1>(a, b, saddr);
+    }
+}
 
 template <int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) probe(int iters, double *sink, double seed) {
@@ -21,10 +37,16 @@ __global__ void __launch_bounds__(THREADS, 1) probe(int iters, double *sink, dou
     for (int k = 0; k < 16; ++k) { a[k] = k * 1e-3 + seed; b[k] = 1.0 + 1e-9 * (threadIdx.x + k) + seed; c[k] = 1e-12 * (k + 1) + seed; }
     const double x = 1.0 + 1e-9 * threadIdx.x + seed, y = 1e-12 + seed;
     unsigned iv = threadIdx.x;
+    __shared__ double2 img[1024];
+    for (int e = threadIdx.x; e < 1024; e += THREADS) img[e] = make_double2(1e-9 * e, 1e-10 * e);
+    __syncthreads();
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(img) + ((MODE == 10) ? (threadIdx.x & 31) * 16u : 0u);
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        const unsigned saddr = sbase + ((unsigned)(it & 7) << 9);
+        if constexpr (MODE >= 9) lds_body<MODE, 0>(a, b, saddr);
 #pragma unroll
-        for (int q = 0; q < 64; ++q) {
+        for (int q = 0; q < (MODE >= 9 ? 0 : 64); ++q) {
             const int i = q & 15, j = (q * 5 + 3) & 15, k = (q * 7 + 1) & 15;
             if (MODE == 0) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[i]) : "d"(x), "d"(y));
             if (MODE == 1) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a[i]) : "d"(b[j]), "d"(c[k]));
@@ -81,5 +103,8 @@ int main() {
     run<1, 768>("DFMA 3 distinct sources", sms, sink);
     run<7, 256>("DFMA a=fma(a,x,y) with an IADD between every two", sms, sink); run<7, 384>("DFMA a=fma(a,x,y) with an IADD between every two", sms, sink);
     run<8, 256>("DFMA a=fma(b_i,c_j,a), 8 accumulators (RAW distance 8)", sms, sink);
+    BOTH(9, "DADD + one LDS.128 (broadcast) per 4 DADD");
+    BOTH(10, "DADD + one LDS.128 (per-lane address) per 4 DADD");
+    BOTH(11, "DADD + one LDS.64 (broadcast) per 2 DADD");
     return 0;
 }

@@ -40,6 +40,7 @@ def main():
     cache = [None, None, None]
     n = {"DFMA": 0, "DMUL": 0, "DADD": 0}
     pipe = rf = both = 0.0
+    lds = 0
     hist = {}
     for _, t in seg + seg:            # two passes: the second one sees the reuse state left by the loop tail
         pass
@@ -48,6 +49,9 @@ def main():
         for _, t in seg:
             t0 = re.sub(r"^@!?U?P\d+\s+", "", t)
             op = t0.split()[0].split(".")[0]
+            if op == "LDS":
+                lds += 1 if rep == 1 else 0
+                continue
             if op not in n:
                 continue                      # (other instructions also read registers; they are few and mostly 32-bit)
             ops = [x.strip() for x in t0.split(None, 1)[1].split(",")][1:]
@@ -69,6 +73,8 @@ def main():
     print(f"  pipe-only bound {pipe:.0f} cycles/iteration, register reads {rf:.0f}, max(pipe, reads) per instruction: {both:.0f} cycles"
           f"  -> ceiling of sm__pipe_fp64_cycles_active = {100.0 * 2 * tot / both:.1f} %")
     print("  (instruction, 64-bit register reads): count ", dict(sorted(hist.items())))
+    # a shared-memory load with one address per warp takes ~1.16 cycles of the SMSP's FP64 issue rate (profiles/r02_rf_probe.txt, modes 9-11)
+    print(f"  {lds} shared-memory loads: +{1.16 * lds:.0f} cycles -> {both + 1.16 * lds:.0f} cycles/iteration, pipe ceiling {100.0 * 2 * tot / (both + 1.16 * lds):.1f} %")
 
 if __name__ == "__main__":
     main()
