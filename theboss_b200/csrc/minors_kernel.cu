@@ -64,11 +64,34 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
 // Complex product of the tree nodes.  The explicit form -- both fused multiply-adds take a.re as their first factor -- is the one of
 // four equivalent spellings for which ptxas schedules the term loop with the fewest three-source DFMAs (scripts/sass_rf.py:
 // 378 / 348 / 311 cycles per term at C = 12 / 11 / 10 against 386 / 350 / 311 for bp_common's cmul; the loop is register-read bound).
-__device__ __forceinline__ cplx k3_cmul(cplx a, cplx b) {
+#ifndef K3_SPELL
+#define K3_SPELL 0
+#endif
+template <int F>
+__device__ __forceinline__ cplx k3_cmul_f(cplx a, cplx b) {
     cplx r;
-    r.re = fma(a.re, b.re, -(a.im * b.im));
-    r.im = fma(a.re, b.im, a.im * b.re);
+    if constexpr ((F & 1) == 0) r.re = fma(a.re, b.re, -(a.im * b.im)); else r.re = fma(-a.im, b.im, a.re * b.re);
+    if constexpr ((F & 2) == 0) r.im = fma(a.re, b.im, a.im * b.re); else r.im = fma(a.im, b.re, a.re * b.im);
     return r;
+}
+__device__ __forceinline__ cplx k3_cmul(cplx a, cplx b) { return k3_cmul_f<0>(a, b); }
+__device__ __forceinline__ cplx k3_cmul_up(cplx a, cplx b) {
+    if constexpr ((K3_SPELL >> 2) & 1) return k3_cmul_f<K3_SPELL & 3>(b, a); else return k3_cmul_f<K3_SPELL & 3>(a, b);
+}
+__device__ __forceinline__ cplx k3_cmul_down(cplx a, cplx b) {
+    if constexpr ((K3_SPELL >> 5) & 1) return k3_cmul_f<(K3_SPELL >> 3) & 3>(b, a); else return k3_cmul_f<(K3_SPELL >> 3) & 3>(a, b);
+}
+__device__ __forceinline__ void k3_leaf_acc(double &acc_re, double &acc_im, cplx x0, cplx y0) {
+    const cplx x = ((K3_SPELL >> 6) & 1) ? y0 : x0, y = ((K3_SPELL >> 6) & 1) ? x0 : y0;
+    if constexpr (((K3_SPELL >> 7) & 3) == 0) {
+        acc_re = fma(x.re, y.re, acc_re); acc_re = fma(-x.im, y.im, acc_re); acc_im = fma(x.re, y.im, acc_im); acc_im = fma(x.im, y.re, acc_im);
+    } else if constexpr (((K3_SPELL >> 7) & 3) == 1) {
+        acc_re = fma(x.re, y.re, acc_re); acc_im = fma(x.re, y.im, acc_im); acc_re = fma(-x.im, y.im, acc_re); acc_im = fma(x.im, y.re, acc_im);
+    } else if constexpr (((K3_SPELL >> 7) & 3) == 2) {
+        acc_re = fma(x.re, y.re, acc_re); acc_im = fma(y.re, x.im, acc_im); acc_re = fma(-x.im, y.im, acc_re); acc_im = fma(y.im, x.re, acc_im);
+    } else {
+        acc_re = fma(x.re, y.re, acc_re); acc_im = fma(x.im, y.re, acc_im); acc_im = fma(x.re, y.im, acc_im); acc_re = fma(-x.im, y.im, acc_re);
+    }
 }
 template <int C, int LO, int HI>
 __device__ __forceinline__ cplx k3_tree_val(const double (&cr)[C], const double (&ci)[C], const cplx (&node)[C]) {
@@ -81,7 +104,7 @@ __device__ __forceinline__ void k3_tree_up(const double (&cr)[C], const double (
         constexpr int MID = (LO + HI) / 2;
         k3_tree_up<C, LO, MID, true>(cr, ci, node);
         k3_tree_up<C, MID, HI, true>(cr, ci, node);
-        if constexpr (ROOT) node[MID] = k3_cmul(k3_tree_val<C, LO, MID>(cr, ci, node), k3_tree_val<C, MID, HI>(cr, ci, node));
+        if constexpr (ROOT) node[MID] = k3_cmul_up(k3_tree_val<C, LO, MID>(cr, ci, node), k3_tree_val<C, MID, HI>(cr, ci, node));
     }
 }
 template <int C, int LO, int HI>
@@ -91,10 +114,17 @@ __device__ __forceinline__ void k3_tree_down(cplx out, const double (&cr)[C], co
     else {
         constexpr int MID = (LO + HI) / 2;
         const cplx L = k3_tree_val<C, LO, MID>(cr, ci, node), R = k3_tree_val<C, MID, HI>(cr, ci, node);
-        if constexpr (MID - LO == 1) cmul_acc(ar[LO], ai[LO], out, R);
-        else k3_tree_down<C, LO, MID>(k3_cmul(out, R), cr, ci, node, ar, ai);
-        if constexpr (HI - MID == 1) cmul_acc(ar[MID], ai[MID], out, L);
-        else k3_tree_down<C, MID, HI>(k3_cmul(out, L), cr, ci, node, ar, ai);
+        if constexpr (((K3_SPELL >> 9) & 1) == 0) {
+            if constexpr (MID - LO == 1) k3_leaf_acc(ar[LO], ai[LO], out, R);
+            else k3_tree_down<C, LO, MID>(k3_cmul_down(out, R), cr, ci, node, ar, ai);
+            if constexpr (HI - MID == 1) k3_leaf_acc(ar[MID], ai[MID], out, L);
+            else k3_tree_down<C, MID, HI>(k3_cmul_down(out, L), cr, ci, node, ar, ai);
+        } else {
+            if constexpr (HI - MID == 1) k3_leaf_acc(ar[MID], ai[MID], out, L);
+            else k3_tree_down<C, MID, HI>(k3_cmul_down(out, L), cr, ci, node, ar, ai);
+            if constexpr (MID - LO == 1) k3_leaf_acc(ar[LO], ai[LO], out, R);
+            else k3_tree_down<C, LO, MID>(k3_cmul_down(out, R), cr, ci, node, ar, ai);
+        }
     }
 }
 // root of the downward pass when the outside factor is the real term weight w (a lane that owns every column)
