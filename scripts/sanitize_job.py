@@ -22,6 +22,7 @@ def occ(m, n):
 print("K1", h.glynn_matrix(workloads.c4_matrix(12)), h.glynn_matrix(workloads.c4_matrix(23)))
 A = workloads.c4_matrix(24)
 print("K1 range", h.glynn_matrix_range(A, 100, 70000)[:2])
+print("K1 wide", h.glynn_matrix_range(workloads.c4_matrix(36), 0, 1 << 17)[:2], h.glynn_matrix_range(workloads.c4_matrix(39), 64, (1 << 16) + 64)[:2])
 dA = torch.from_numpy(np.ascontiguousarray(A).view(np.float64).reshape(-1).copy()).cuda()
 d_all = torch.zeros(4, dtype=torch.float64, device="cuda")
 hx = _native.Handle(0)

@@ -19,9 +19,9 @@ def orc():
     return pyoracle
 
 
-@pytest.mark.parametrize("N", [23, 34, 35, 37])
+@pytest.mark.parametrize("N", [23, 34, 35, 36, 37])
 def test_scaled_permutation_matrices_at_the_size_limits(handle, N):
-    """perm(D P) = prod(d) exactly; N = 23 / 34 bracket the block-4 bulk kernel, 35+ use the generic one.
+    """perm(D P) = prod(d) exactly; N = 23 / 34 bracket the block-4 bulk kernel, 35+ run the warp-pair kernel (odd N: halves of 18 + 17 columns).
     (2^(N-1) equal-magnitude terms cancelling down to 2^(N-1) prod(d): a harsh accumulation test.)"""
     rng = np.random.RandomState(N)
     d = np.exp(1j * rng.uniform(0, 2 * np.pi, N)) * rng.uniform(0.8, 1.2, N)

@@ -69,6 +69,33 @@ def test_range_partials_cover_the_term_space(handle, orc, N, shards):
     assert _rel(total / T, handle.glynn_matrix(A)) <= 1e-13
 
 
+@pytest.mark.parametrize("N", [35, 36, 39, 40])
+def test_wide_matrices_on_step_ranges_vs_oracle(handle, orc, N):
+    """N = 35 ... 40 (glynn_pair4_kernel: two warps share the columns of a Gray stream and trade half-products under a named barrier):
+    partial sums over step ranges against the 80-bit oracle -- aligned bulk, bulk + unaligned head and tail (generic kernel), a range
+    deep inside the term space (rows >= 30 flip), and one short enough to leave most warp pairs without work."""
+    A = workloads.c4_matrix(N)
+    for lo, hi in ((0, 1 << 18), (1 << 20, (1 << 20) + (1 << 17)), (3, (1 << 17) + 77), ((1 << 30) + 4096, (1 << 30) + 4096 + (1 << 16)),
+                   ((1 << (N - 1)) - (1 << 16), 1 << (N - 1))):
+        p = handle.glynn_matrix_range(A, lo, hi)
+        got = complex(p[0] + p[1], p[2] + p[3])
+        want = orc.glynn_range(A, lo, hi, "ld")
+        # (partial sums cancel less than the permanent: 1e-11 of the largest term magnitude is the meaningful bar)
+        assert abs(got - want) <= 1e-11 * max(abs(want), 1e-3 * abs(got) + 1e-300), (N, lo, hi, got, want)
+
+
+def test_wide_matrix_shards_agree_with_the_unsharded_walk(handle):
+    """The multi-GPU split at N = 36: eight range partials over 2^24 steps sum to the partial of the whole range (both through the
+    warp-pair kernel, different spans per lane)."""
+    A = workloads.c4_matrix(36)
+    T = 1 << 24
+    whole = handle.glynn_matrix_range(A, 0, T)
+    parts = [handle.glynn_matrix_range(A, T * i // 8, T * (i + 1) // 8) for i in range(8)]
+    tot = sum(complex(p[0] + p[1], p[2] + p[3]) for p in parts)
+    ref = complex(whole[0] + whole[1], whole[2] + whole[3])
+    assert abs(tot - ref) <= 1e-12 * abs(ref)
+
+
 def test_unaligned_ranges(handle, orc):
     A = workloads.c4_matrix(11)
     for lo, hi in [(0, 1), (1, 2), (3, 70), (65, 129), (17, 1024), (1000, 1024), (5, 5)]:

@@ -339,6 +339,157 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
     k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd, x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// wide bulk kernel (K1W_MIN_N <= N <= BP_MAX_N): the block-4 layout with the COLUMNS of a Gray stream split over two warps
+// ---------------------------------------------------------------------------------------------
+// Beyond N = 34 the 4N registers of the column sums leave no room for the four-step body (profiles/r02_k1_wide_n.txt: spills,
+// 0.33 .. 0.38 of peak against 0.46 for the generic kernel).  Here warps 2p and 2p + 1 of a block walk the SAME 32 Gray streams
+// (lane = stream), the even warp over columns [0, H), the odd one over [H, N), H = ceil(N / 2): 2H <= 40 registers of sums per
+// lane, row 0 still comes from the constant bank with compile-time addresses (the half is warp-uniform: each warp takes
+// its own copy of the loop), and once per four steps the two warps trade half-products through shared memory under
+// named barriers -- the even warp accumulates the first two steps of a block of four, the odd one the last two, so the FP64 work is
+// the (6N - 4) instructions per step of the one-lane layout.  Two alternating exchange buffers make one rendezvous per
+// iteration enough (a warp cannot be two iterations ahead of its partner).  Trip counts are block-uniform (span / 4
+// iterations for every lane; steps at or beyond `end` are computed but not accumulated), so no lane skips a barrier.
+#define K1W_MIN_N 35
+#define K1W_THREADS 128
+#define K1W_MINB 3
+
+// (H = ceil(N / 2) registers pairs per lane in both halves; a half owns the HC <= H columns [C0, C0 + HC))
+template <int H, int HC>
+__device__ __forceinline__ cplx k1w_half_product(const double (&sr)[H], const double (&si)[H]) {
+    cplx p = {sr[0], si[0]};
+#pragma unroll
+    for (int j = 1; j < HC; ++j) {   // (both fused multiply-adds on p.re: the spelling with the fewest three-source DFMAs, scripts/sass_rf.py)
+        cplx q = {sr[j], si[j]}, t;
+        t.re = fma(p.re, q.re, -(p.im * q.im)); t.im = fma(p.re, q.im, p.im * q.re);
+        p = t;
+    }
+    return p;
+}
+// Row 0 as constant-bank operands of the DADDs.  `r0` is c_A2 plus an offset that is always zero but formally depends on the loop
+// counter: loop-INVARIANT constant loads are hoisted out of the step loop by ptxas -- into uniform registers while they last, then
+// into vector registers that it spills (measured: 230 .. 690 bytes of spills at every register cap) -- whereas loop-variant ones
+// are re-issued per use as uniform loads (LDCU.128) feeding the FP64 instructions directly, the block-4 kernel's pattern.
+template <int H, int C0, int HC, int MODE>   // MODE 0: subtract, 1: add
+__device__ __forceinline__ void k1w_flip_row0(const double2 *r0, double (&sr)[H], double (&si)[H]) {
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+        if (MODE == 0) { sr[j] -= r0[C0 + j].x; si[j] -= r0[C0 + j].y; }
+        else           { sr[j] += r0[C0 + j].x; si[j] += r0[C0 + j].y; }
+    }
+}
+// sums += sg * row (shared memory), or += row when SIGNED rows are stored
+template <int H, int HC, bool FMA>
+__device__ __forceinline__ void k1w_add_row(const double2 *row, double sg, double (&sr)[H], double (&si)[H]) {
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+        const double2 v = row[j];
+        if (FMA) { sr[j] = fma(sg, v.x, sr[j]); si[j] = fma(sg, v.y, si[j]); }
+        else     { sr[j] += v.x; si[j] += v.y; }
+    }
+}
+// steps I0 + 1 .. I0 + 3 of an aligned block of four on one half's columns: rows 0, 1, 0; new delta = -1, (bit 2 of I0 ? +1 : -1), +1.
+// Row 1 comes from a signed image in shared memory (+row 1, -row 1): as a constant-bank operand of a run-time-signed DFMA (the
+// block-4 kernel's form) ptxas hoists the whole row out of the loop into registers and spills them here.
+template <int N, int H, int C0, int HC>
+__device__ __forceinline__ void k1w_three_steps(uint64_t I0, const double2 *r0, const double2 *srow1, double (&sr)[H], double (&si)[H],
+                                                cplx &p1, cplx &p2, cplx &p3) {
+    k1w_flip_row0<H, C0, HC, 0>(r0, sr, si);
+    p1 = k1w_half_product<H, HC>(sr, si);
+    k1w_add_row<H, HC, false>(srow1 + (((I0 >> 2) & 1ull) ? 0 : N) + C0, 0.0, sr, si);
+    p2 = k1w_half_product<H, HC>(sr, si);
+    k1w_flip_row0<H, C0, HC, 1>(r0, sr, si);
+    p3 = k1w_half_product<H, HC>(sr, si);
+}
+
+// The walk of one warp.  HALF = 0: columns [0, H), accumulates the first two steps of every block of four; HALF = 1: columns [H, N),
+// the last two.  Each half is its own straight-line loop (compile-time column offsets).  The exchange is the producer / consumer
+// pattern of named barriers: a warp ARRIVES on the barrier its partner waits on (its two half-products are in shared memory) and
+// SYNCS on its own (the partner's are) -- 32 arriving + 32 waiting threads per barrier.  Like the exchange buffers the barrier ids
+// alternate between two sets with the parity of the iteration: a warp that runs ahead arrives on the OTHER set, never on a barrier
+// whose previous phase its partner has not left yet (four ids per pair).
+// xmine / xpeer: this lane's slots [buffer][product] in the exchange area, written by this warp / by the partner warp.
+template <int N, int HALF>
+__device__ __forceinline__ void k1w_walk(const double2 *sA2, const double2 *srow1, uint64_t start, uint64_t end, unsigned iters,
+                                         double2 *xmine, const double2 *xpeer, int bar_mine, int bar_peer, dd &acc_re, dd &acc_im) {
+    constexpr int H = (N + 1) / 2, C0 = HALF ? H : 0, HC = HALF ? N - H : H;
+    constexpr int XS = 2 * 32;                       // double2s between the two buffers of a lane
+    double sr[H], si[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+    const uint64_t g0 = start ^ (start >> 1);
+#pragma unroll 1
+    for (int i = 0; i < N; ++i)
+        k1w_add_row<H, HC, true>(sA2 + i * N + C0, ((g0 >> i) & 1ull) ? -0.5 : 0.5, sr, si);
+    double wr = 0.0, wi = 0.0;
+    uint64_t I0 = start;
+    cplx p0 = k1w_half_product<H, HC>(sr, si);                           // step I0 (even: +)
+#pragma unroll 1
+    for (unsigned it = 0; it < iters; ++it) {
+        const bool live = I0 < end;                                       // spans end on multiples of 4: a block of steps is in or out
+        const double2 *r0 = c_A2 + __any_sync(0xffffffffu, it >> 30);     // = c_A2: a warp vote keeps the zero in the uniform datapath (see k1w_flip_row0)
+        cplx p1, p2, p3;
+        k1w_three_steps<N, H, C0, HC>(I0, r0, srow1, sr, si, p1, p2, p3);
+        double2 *mine = xmine + (it & 1u) * XS;
+        const double2 *peer = xpeer + (it & 1u) * XS;
+        if (HALF == 0) { mine[0] = make_double2(p2.re, p2.im); mine[32] = make_double2(p3.re, p3.im); }
+        else           { mine[0] = make_double2(p0.re, p0.im); mine[32] = make_double2(p1.re, p1.im); }
+        __threadfence_block();                                             // the stores above before the arrival
+        __syncwarp();                                                      // (the flush / `live` branches of the previous iteration are per-lane)
+        asm volatile("bar.arrive %0, 64;\n\tbar.sync %1, 64;" :: "r"(bar_peer + 2 * (int)(it & 1u)), "r"(bar_mine + 2 * (int)(it & 1u)) : "memory");
+        const double2 qa = peer[0], qb = peer[32];
+        const cplx a = {qa.x, qa.y}, b = {qb.x, qb.y};
+        if (live) {
+            if (HALF == 0) { cmul_acc(wr, wi, p0, a); cmul_sub(wr, wi, p1, b); }
+            else           { cmul_acc(wr, wi, p2, a); cmul_sub(wr, wi, p3, b); }
+        }
+        I0 += 4;
+        if (((uint32_t)I0 & 63u) == 0u) {
+            acc_re = dd_add_d(acc_re, wr); acc_im = dd_add_d(acc_im, wi);
+            wr = 0.0; wi = 0.0;
+        }
+        // step I0 (block-closing flip): run-time row >= 2, per-lane sign
+        const uint32_t Il = (uint32_t)I0;
+        const int r = Il ? (__ffs((int)Il) - 1) : (31 + __ffs((int)(uint32_t)(I0 >> 32)));
+        const double2 *row = sA2 + (r < N ? r : 0) * N + C0;             // (r >= N only on blocks past the end of the term space: not accumulated)
+        k1w_add_row<H, HC, true>(row, ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0, sr, si);
+        p0 = k1w_half_product<H, HC>(sr, si);
+    }
+    acc_re = dd_add_d(acc_re, wr);
+    acc_im = dd_add_d(acc_im, wi);
+}
+
+// lo and hi are multiples of 64, span a multiple of 32; one Gray stream per lane of a warp PAIR (K1W_THREADS / 2 streams per block)
+template <int N>
+__global__ void __launch_bounds__(K1W_THREADS, K1W_MINB)
+glynn_pair4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
+                   double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd, const K1Exchange x) {
+    __shared__ double2 sA2[N * N];
+    __shared__ double2 xbuf[(K1W_THREADS / 64) * 2 * 2 * 2 * 32];       // [pair][half][buffer][product][lane]
+    __shared__ double red[4 * (K1W_THREADS / 32)];
+    __shared__ double2 srow1[2 * N];                                       // +row 1, -row 1
+    for (int e = threadIdx.x; e < N * N; e += K1W_THREADS) sA2[e] = reinterpret_cast<const double2 *>(A)[e];
+    for (int e = threadIdx.x; e < N; e += K1W_THREADS) {
+        const double2 v = reinterpret_cast<const double2 *>(A)[N + e];
+        srow1[e] = v; srow1[N + e] = make_double2(-v.x, -v.y);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = warp & 1, pair = warp >> 1;
+    const uint64_t stream = (uint64_t)blockIdx.x * (K1W_THREADS / 2) + (uint64_t)(pair * 32 + lane);
+    const uint64_t start = lo + stream * span;                            // (may lie beyond hi: the lane still keeps its partner company)
+    const uint64_t end = (start >= hi) ? start : ((hi - start < span) ? hi : start + span);
+    const unsigned iters = (unsigned)(span >> 2);
+    double2 *xmine = xbuf + ((pair * 2 + half) * 4) * 32 + lane;
+    const double2 *xpeer = xbuf + ((pair * 2 + (half ^ 1)) * 4) * 32 + lane;
+    dd acc_re = {0.0, 0.0}, acc_im = {0.0, 0.0};
+    // barrier ids 1 + 4 pair (+ 2 on odd iterations): the even warp waits on it; 2 + 4 pair (+ 2): the odd warp does; id 0 is __syncthreads
+    if (half == 0) k1w_walk<N, 0>(sA2, srow1, start, end, iters, xmine, xpeer, 1 + 4 * pair, 2 + 4 * pair, acc_re, acc_im);
+    else           k1w_walk<N, 1>(sA2, srow1, start, end, iters, xmine, xpeer, 2 + 4 * pair, 1 + 4 * pair, acc_re, acc_im);
+    block_reduce_dd(acc_re, acc_im, red);
+    k1_block_epilogue(acc_re, acc_im, partials, counter, N, out_dd, x);
+}
+
 // Sums the partials of several kernels (bulk + unaligned head / tail) in block order; one warp.
 __global__ void glynn_finish_kernel(const double *__restrict__ partials, int nblocks, int scale_log2,
                                     double *__restrict__ out_dd, const K1Exchange x) {
@@ -354,12 +505,14 @@ typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *, un
 
 static k1_fn g_k1_fn[BP_MAX_N + 1], g_k1_bulk[BP_MAX_N + 1];
 static int g_k1_minb[BP_MAX_N + 1], g_k1_bulk_threads[BP_MAX_N + 1];
+static int g_k1_bulk_streams[BP_MAX_N + 1], g_k1_bulk_blocks[BP_MAX_N + 1];   // Gray streams per block, resident blocks per SM
 
 template <int N>
 static void k1_entry(k1_fn *fn, int *minb, k1_fn *bulk) {
     fn[N] = glynn_gray_kernel<N>;
     minb[N] = K1Cfg<N>::MINB;
-    if constexpr (N >= K1B_MIN_N && N <= K1B_MAX_N) { bulk[N] = glynn_block4_kernel<N>; g_k1_bulk_threads[N] = K1BCfg<N>::THREADS; }
+    if constexpr (N >= K1B_MIN_N && N <= K1B_MAX_N) { bulk[N] = glynn_block4_kernel<N>; g_k1_bulk_threads[N] = K1BCfg<N>::THREADS; g_k1_bulk_streams[N] = K1BCfg<N>::THREADS; g_k1_bulk_blocks[N] = 1; }
+    if constexpr (N >= K1W_MIN_N) { bulk[N] = glynn_pair4_kernel<N>; g_k1_bulk_threads[N] = K1W_THREADS; g_k1_bulk_streams[N] = K1W_THREADS / 2; g_k1_bulk_blocks[N] = K1W_MINB; }
     if constexpr (N > 1) k1_entry<N - 1>(fn, minb, bulk);
 }
 
@@ -408,7 +561,7 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
     uint64_t blo = (lo + 63) & ~63ull, bhi = hi & ~63ull;
     const bool bulk = g_k1_bulk[N] != nullptr && bhi > blo && (bhi - blo) >= (1ull << 16) && h->device < 64;
     if (!bulk) { blo = hi; bhi = hi; }
-    const int bulk_grid_max = h->sm_count;
+    const int bulk_grid_max = h->sm_count * (g_k1_bulk[N] ? g_k1_bulk_blocks[N] : 1);
     const int gen_grid_max = h->sm_count * g_k1_minb[N];
     int rc = bp_reserve(h, BP_SLOT_PARTIALS, sizeof(double) * 4 * (size_t)(bulk_grid_max + 2 * gen_grid_max + 8));
     if (rc) return rc;
@@ -436,14 +589,14 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
     if (bulk) {
         const size_t bytes = sizeof(double2) * (size_t)N * N;
         const uint64_t total = bhi - blo;
-        const int bthreads = g_k1_bulk_threads[N];
-        const uint64_t threads = (uint64_t)bulk_grid_max * bthreads;
+        const int bthreads = g_k1_bulk_threads[N], bstreams = g_k1_bulk_streams[N];
+        const uint64_t threads = (uint64_t)bulk_grid_max * bstreams;                 // Gray streams in flight
         // spans are multiples of 32 steps: lanes of a warp then differ by a multiple of 32, so inside a warp only the
         // block-closing flips at multiples of 32 (1 block in 8) read two different rows; the finer grain keeps the load
         // balance above 99 % when the range is cut over 8 GPUs (2^26 steps over 56832 threads = 1180.8 per thread)
         uint64_t span = (total + threads - 1) / threads;
         span = ((span + 31) / 32) * 32;
-        const int grid = (int)(((total + span - 1) / span + bthreads - 1) / bthreads);
+        const int grid = (int)(((total + span - 1) / span + bstreams - 1) / bstreams);
         {
             std::lock_guard<std::mutex> g(g_const_mutex);
             K1ConstOwner &own = g_const_owner[h->device];
