@@ -13,11 +13,12 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_exchange_with_a_single_rank_returns_the_range_partial():
+@pytest.mark.parametrize("N", [24, 36])
+def test_exchange_with_a_single_rank_returns_the_range_partial(N):
+    """(N = 24: block-4 bulk kernel; N = 36: the warp-pair kernel -- the exchange runs in whichever kernel finishes the sum)"""
     import torch
     from theboss_b200 import _native
     h = _native.Handle(0)
-    N = 24
     A = workloads.c4_matrix(N)
     dA = torch.from_numpy(np.ascontiguousarray(A).view(np.float64).reshape(-1).copy()).cuda()
     d_part = torch.zeros(4, dtype=torch.float64, device="cuda")
@@ -25,7 +26,7 @@ def test_exchange_with_a_single_rank_returns_the_range_partial():
     ipc = h.exchange_create(1, 0)
     assert len(ipc) == 64
     h.exchange_connect([ipc])
-    for lo, hi in ((0, 1 << (N - 1)), (64, 1 << 20), (100, 5000), (7, 7)):      # bulk kernel, bulk + tails, generic, empty
+    for lo, hi in ((0, 1 << min(N - 1, 24)), (64, 1 << 20), (100, 5000), (7, 7)):      # bulk kernel, bulk + tails, generic, empty
         h.glynn_matrix_range_dev(dA.data_ptr(), N, lo, hi, d_part.data_ptr())
         h.glynn_matrix_range_exchange(dA.data_ptr(), N, lo, hi, d_all.data_ptr())
         h.synchronize()
