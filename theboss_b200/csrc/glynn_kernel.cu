@@ -354,6 +354,7 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
 #define K1W_MIN_N 35
 #define K1W_THREADS 128
 #define K1W_MINB 3
+static_assert(4 * (K1W_THREADS / 64) <= 15, "four named barriers per warp pair, ids 1 .. 15");
 
 // (H = ceil(N / 2) registers pairs per lane in both halves; a half owns the HC <= H columns [C0, C0 + HC))
 template <int H, int HC>
