@@ -120,6 +120,12 @@ int bp_exchange_connect(bp_handle h, const unsigned char *ipc_handles /* [world]
 int bp_exchange_destroy(bp_handle h);
 int bp_glynn_matrix_range_exchange(bp_handle h, const double *dA, int N, uint64_t step_lo, uint64_t step_hi,
                                    double *d_out_all);
+/* The same collective with HOST buffers, as one call (what a sharded GlynnGrayPermanentCalculator.compute_permanent pays per
+ * permanent, glynn_gray_permanent_calculator.py:41-71): A (N x N, row-major complex128 on the host) goes through the handle's pinned
+ * staging buffer to the device, the kernel runs this rank's slice and the exchange, and all ranks' partials come back to
+ * out_all[world][4] (host); returns after the stream has drained.  With world == 1 it equals bp_glynn_matrix_range. */
+int bp_glynn_matrix_range_exchange_host(bp_handle h, const double *A, int N, uint64_t step_lo, uint64_t step_hi,
+                                        double *out_all);
 
 /* Full calculator call: builds the effective scattering matrix of (U, s, t) on the device
  * (boson_sampling_utilities.py:595-626) and evaluates it.  s, t: length m occupations.

@@ -31,9 +31,16 @@ def test_exchange_with_a_single_rank_returns_the_range_partial(N):
         h.glynn_matrix_range_exchange(dA.data_ptr(), N, lo, hi, d_all.data_ptr())
         h.synchronize()
         assert torch.equal(d_part.cpu(), d_all.cpu()), (lo, hi)
+    # host-buffer form of the collective: one call, same bits
+    for lo, hi in ((0, 1 << 20), (100, 5000)):
+        want = h.glynn_matrix_range(A, lo, hi)
+        got = h.glynn_matrix_range_exchange_host(A, lo, hi, 1)
+        assert got.shape == (1, 4) and tuple(got[0]) == tuple(want)
     h.exchange_destroy()
     with pytest.raises(_native.BossPermError):
         h.glynn_matrix_range_exchange(dA.data_ptr(), N, 0, 64, d_all.data_ptr())
+    with pytest.raises(_native.BossPermError):
+        h.glynn_matrix_range_exchange_host(A, 0, 64, 1)
     h.close()
 
 

@@ -471,6 +471,7 @@ def test_every_entry_point_rejects_a_null_handle_without_touching_the_device():
         "bp_exchange_connect": lambda: lib.bp_exchange_connect(None, (C.c_ubyte * 128)()),
         "bp_exchange_destroy": lambda: lib.bp_exchange_destroy(None),
         "bp_glynn_matrix_range_exchange": lambda: lib.bp_glynn_matrix_range_exchange(None, A.ctypes.data, 2, 0, 2, None),
+        "bp_glynn_matrix_range_exchange_host": lambda: lib.bp_glynn_matrix_range_exchange_host(None, A.ctypes.data, 2, 0, 2, None),
         "bp_glynn_single": lambda: lib.bp_glynn_single(None, A.ctypes.data, 2, s.ctypes.data, s.ctypes.data, out),
         "bp_perm_batched": lambda: lib.bp_perm_batched(None, A.ctypes.data, 2, S.ctypes.data, S.ctypes.data, 1, 1, o.ctypes.data),
         "bp_perm_batched_dev": lambda: lib.bp_perm_batched_dev(None, A.ctypes.data, 2, S.ctypes.data, S.ctypes.data, 1, 1, o.ctypes.data),

@@ -54,6 +54,7 @@ SIGNATURES = {
     "bp_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bp_exchange_destroy": (C.c_int, [C.c_void_p]),
     "bp_glynn_matrix_range_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bp_glynn_matrix_range_exchange_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "bp_glynn_single": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _dp]),
     "bp_perm_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "bp_perm_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
@@ -250,6 +251,18 @@ class Handle:
 
     def glynn_matrix_range_exchange(self, dA_ptr: int, N: int, lo: int, hi: int, d_out_all_ptr: int):
         self._call("bp_glynn_matrix_range_exchange", C.c_void_p(dA_ptr), int(N), int(lo), int(hi), C.c_void_p(d_out_all_ptr))
+
+    def glynn_matrix_range_exchange_host(self, A: np.ndarray, lo: int, hi: int, world: int) -> np.ndarray:
+        """Host-buffer form of the collective: this rank's slice [lo, hi) of the Gray range of A plus the partial exchange, one call;
+        returns all ranks' un-normalised double-double partials, shape (world, 4)."""
+        A = np.ascontiguousarray(A, dtype=np.complex128)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise AttributeError
+        if not 0 <= int(lo) <= int(hi):
+            raise ValueError(f"Gray step range [{lo}, {hi})")
+        out = np.empty((int(world), 4), dtype=np.float64)
+        self._call("bp_glynn_matrix_range_exchange_host", C.c_void_p(A.ctypes.data), int(A.shape[0]), int(lo), int(hi), C.c_void_p(out.ctypes.data))
+        return out
 
     def glynn_single(self, U: np.ndarray, s: np.ndarray, t: np.ndarray) -> complex:
         U, s, t = self._normalised(U, s, t)

@@ -302,6 +302,27 @@ int bp_glynn_matrix_range_exchange(bp_handle h, const double *dA, int N, uint64_
     return bp_k1_launch(h, dA, N, step_lo, step_hi, nullptr, d_out_all);
 }
 
+int bp_glynn_matrix_range_exchange_host(bp_handle h, const double *A, int N, uint64_t step_lo, uint64_t step_hi, double *out_all) {
+    if (!h || !A || !out_all) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_exchange_host: NULL argument");
+    if (N < 1 || N > BP_MAX_N) return bp_fail(h, BP_ERR_UNSUPPORTED, "bp_glynn_matrix_range_exchange_host: N=%d outside [1, %d]", N, BP_MAX_N);
+    if (h->xchg_world < 1) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix_range_exchange_host: call bp_exchange_create / bp_exchange_connect first");
+    BP_ON_DEVICE(h);
+    const size_t bytes = sizeof(double) * 2 * (size_t)N * N, out_bytes = sizeof(double) * 4 * (size_t)h->xchg_world;
+    int rc = bp_reserve(h, BP_SLOT_MATRIX, bytes);
+    if (rc) return rc;
+    if ((rc = bp_reserve(h, BP_SLOT_OUT, out_bytes))) return rc;
+    if ((rc = bp_reserve_pinned(h, bytes + 64 + out_bytes))) return rc;
+    memcpy(h->h_pin, A, bytes);
+    BP_CUDA(h, cudaMemcpyAsync(h->d_buf[BP_SLOT_MATRIX], h->h_pin, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = bp_k1_launch(h, (const double *)h->d_buf[BP_SLOT_MATRIX], N, step_lo, step_hi, nullptr, (double *)h->d_buf[BP_SLOT_OUT]);
+    if (rc) return rc;
+    double *res = (double *)((char *)h->h_pin + ((bytes + 31) / 32) * 32);
+    BP_CUDA(h, cudaMemcpyAsync(res, h->d_buf[BP_SLOT_OUT], out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    BP_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(out_all, res, out_bytes);
+    return BP_OK;
+}
+
 int bp_glynn_matrix(bp_handle h, const double *A, int N, double out[2]) {
     if (!h || !out) return bp_fail(h, BP_ERR_INVALID, "bp_glynn_matrix: NULL argument");
     if (N == 0) { out[0] = 1.0; out[1] = 0.0; return BP_OK; }   // glynn_gray_permanent_calculator.py:52-53

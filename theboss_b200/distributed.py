@@ -168,6 +168,13 @@ class ShardedGlynnPermanent:
         return combine_partials(self.h_all.numpy(), self.N)
 
     def compute(self, A: np.ndarray) -> complex:
+        """One permanent with HOST buffers in and out.  With the peer-memory exchange (or a single rank) this is ONE C-ABI call:
+        staged upload, this rank's slice of K1, the in-kernel exchange, download of all partials."""
+        if self.exchange == "peer":
+            return combine_partials(self.handle.glynn_matrix_range_exchange_host(A, self.lo, self.hi, self.world_size), self.N)
+        if self.world_size == 1:
+            assert np.shape(A) == (self.N, self.N)
+            return combine_partials(np.asarray(self.handle.glynn_matrix_range(A, self.lo, self.hi), dtype=np.float64).reshape(1, 4), self.N)
         self.upload(A)
         self.enqueue_resident()
         return self.finish()
