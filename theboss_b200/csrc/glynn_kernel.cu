@@ -236,6 +236,11 @@ template <int N>
 struct K1BCfg {
     static constexpr int THREADS = (N <= 30) ? 384 : 256;
     static constexpr int NCH = (N <= 30) ? 1 : 2;
+    // Run-time row flips (every fourth step) as DADDs of a SIGNED shared-memory image (A, then -A) instead of sign x row DFMAs: a
+    // DADD takes 2.0 cycles of the pipe where a DFMA takes 2.18 (profiles/r02_rf_probe.txt).  Measured per N (profiles/r02_k1_wide_n.txt):
+    // +1.5 .. +6 % for N = 25 .. 27, 29, 31 .. 34, no change at 23, 24, 28, and -3.3 % at N = 30, where ptxas pairs fewer DFMAs of the
+    // product chain in the instantiation with the image -- that one keeps the DFMA form.
+    static constexpr bool SIGNED_ROWS = (N != 30);
 };
 
 __constant__ double2 c_A2[BP_MAX_N * BP_MAX_N];   // A of the permanent in flight (row stride N)
@@ -278,9 +283,14 @@ __global__ void __launch_bounds__(K1BCfg<N>::THREADS, 1)
 glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
                     double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd, const K1Exchange x) {
     constexpr int THREADS = K1BCfg<N>::THREADS;
-    __shared__ double2 sA2[N * N];
+    constexpr bool SIGNED = K1BCfg<N>::SIGNED_ROWS;
+    __shared__ double2 sA2[(SIGNED ? 2 : 1) * N * N];                // A (and -A)
     __shared__ double red[4 * (THREADS / 32)];
-    for (int e = threadIdx.x; e < N * N; e += THREADS) sA2[e] = reinterpret_cast<const double2 *>(A)[e];
+    for (int e = threadIdx.x; e < N * N; e += THREADS) {
+        const double2 v = reinterpret_cast<const double2 *>(A)[e];
+        sA2[e] = v;
+        if constexpr (SIGNED) sA2[N * N + e] = make_double2(-v.x, -v.y);
+    }
     __syncthreads();
     const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
     const uint64_t start = lo + gtid * span;
@@ -322,13 +332,23 @@ glynn_block4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint
             // step I0 (block-closing flip): run-time row >= 2, per-thread sign
             const uint32_t Il = (uint32_t)I0;
             const int r = Il ? (__ffs((int)Il) - 1) : (31 + __ffs((int)(uint32_t)(I0 >> 32)));
-            const double sg = ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0;
-            const double2 *row = sA2 + r * N;
+            if constexpr (SIGNED) {
+                const double2 *row = sA2 + (r + (((I0 >> (r + 1)) & 1ull) ? 0 : N)) * N;
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 a = row[j];
-                sr[j] = fma(sg, a.x, sr[j]);
-                si[j] = fma(sg, a.y, si[j]);
+                for (int j = 0; j < N; ++j) {
+                    const double2 a = row[j];
+                    sr[j] += a.x;
+                    si[j] += a.y;
+                }
+            } else {
+                const double sg = ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0;
+                const double2 *row = sA2 + r * N;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double2 a = row[j];
+                    sr[j] = fma(sg, a.x, sr[j]);
+                    si[j] = fma(sg, a.y, si[j]);
+                }
             }
             k1b_product_acc<N, true>(sr, si, wr, wi);
         }
@@ -453,8 +473,8 @@ __device__ __forceinline__ void k1w_walk(const double2 *sA2, const double2 *srow
         // step I0 (block-closing flip): run-time row >= 2, per-lane sign
         const uint32_t Il = (uint32_t)I0;
         const int r = Il ? (__ffs((int)Il) - 1) : (31 + __ffs((int)(uint32_t)(I0 >> 32)));
-        const double2 *row = sA2 + (r < N ? r : 0) * N + C0;             // (r >= N only on blocks past the end of the term space: not accumulated)
-        k1w_add_row<H, HC, true>(row, ((I0 >> (r + 1)) & 1ull) ? 1.0 : -1.0, sr, si);
+        const double2 *row = sA2 + ((r < N ? r : 0) + (((I0 >> (r + 1)) & 1ull) ? 0 : N)) * N + C0;   // (r >= N only past the end of the term space: not accumulated)
+        k1w_add_row<H, HC, false>(row, 0.0, sr, si);
         p0 = k1w_half_product<H, HC>(sr, si);
     }
     acc_re = dd_add_d(acc_re, wr);
@@ -466,11 +486,15 @@ template <int N>
 __global__ void __launch_bounds__(K1W_THREADS, K1W_MINB)
 glynn_pair4_kernel(const double *__restrict__ A, uint64_t lo, uint64_t hi, uint64_t span,
                    double *__restrict__ partials, unsigned int *counter, double *__restrict__ out_dd, const K1Exchange x) {
-    __shared__ double2 sA2[N * N];
+    extern __shared__ __align__(16) unsigned char k1w_dyn[];
+    double2 *sA2 = reinterpret_cast<double2 *>(k1w_dyn);                 // A, then -A: run-time row flips add a signed row (K1W_SMEM bytes)
     __shared__ double2 xbuf[(K1W_THREADS / 64) * 2 * 2 * 2 * 32];       // [pair][half][buffer][product][lane]
     __shared__ double red[4 * (K1W_THREADS / 32)];
     __shared__ double2 srow1[2 * N];                                       // +row 1, -row 1
-    for (int e = threadIdx.x; e < N * N; e += K1W_THREADS) sA2[e] = reinterpret_cast<const double2 *>(A)[e];
+    for (int e = threadIdx.x; e < N * N; e += K1W_THREADS) {
+        const double2 v = reinterpret_cast<const double2 *>(A)[e];
+        sA2[e] = v; sA2[N * N + e] = make_double2(-v.x, -v.y);
+    }
     for (int e = threadIdx.x; e < N; e += K1W_THREADS) {
         const double2 v = reinterpret_cast<const double2 *>(A)[N + e];
         srow1[e] = v; srow1[N + e] = make_double2(-v.x, -v.y);
@@ -507,13 +531,14 @@ typedef void (*k1_fn)(const double *, uint64_t, uint64_t, uint64_t, double *, un
 static k1_fn g_k1_fn[BP_MAX_N + 1], g_k1_bulk[BP_MAX_N + 1];
 static int g_k1_minb[BP_MAX_N + 1], g_k1_bulk_threads[BP_MAX_N + 1];
 static int g_k1_bulk_streams[BP_MAX_N + 1], g_k1_bulk_blocks[BP_MAX_N + 1];   // Gray streams per block, resident blocks per SM
+static int g_k1_bulk_smem[BP_MAX_N + 1];                                       // dynamic shared memory of the bulk kernel (wide kernel: signed image of A)
 
 template <int N>
 static void k1_entry(k1_fn *fn, int *minb, k1_fn *bulk) {
     fn[N] = glynn_gray_kernel<N>;
     minb[N] = K1Cfg<N>::MINB;
     if constexpr (N >= K1B_MIN_N && N <= K1B_MAX_N) { bulk[N] = glynn_block4_kernel<N>; g_k1_bulk_threads[N] = K1BCfg<N>::THREADS; g_k1_bulk_streams[N] = K1BCfg<N>::THREADS; g_k1_bulk_blocks[N] = 1; }
-    if constexpr (N >= K1W_MIN_N) { bulk[N] = glynn_pair4_kernel<N>; g_k1_bulk_threads[N] = K1W_THREADS; g_k1_bulk_streams[N] = K1W_THREADS / 2; g_k1_bulk_blocks[N] = K1W_MINB; }
+    if constexpr (N >= K1W_MIN_N) { bulk[N] = glynn_pair4_kernel<N>; g_k1_bulk_threads[N] = K1W_THREADS; g_k1_bulk_streams[N] = K1W_THREADS / 2; g_k1_bulk_blocks[N] = K1W_MINB; g_k1_bulk_smem[N] = 2 * N * N * (int)sizeof(double2); }
     if constexpr (N > 1) k1_entry<N - 1>(fn, minb, bulk);
 }
 
@@ -615,7 +640,11 @@ int bp_k1_launch(bp_context *h, const double *dA, int N, uint64_t lo, uint64_t h
                 BP_CUDA(h, cudaMemcpyToSymbolAsync(c_A2, dA, bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
                 own.h = h; own.dA = dA; own.N = N; own.gen = (h->resident_A == dA) ? h->resident_gen : ~0ull;
             }
-            g_k1_bulk[N]<<<grid, bthreads, 0, h->stream>>>(dA, blo, bhi, span, d_partials, d_counter, d_out_dd, xs);
+            if (g_k1_bulk_smem[N] > 0) {   // (up to 51 KB of dynamic + 10 KB of static shared memory: beyond the 48 KB that need no opt-in)
+                cudaError_t e = cudaFuncSetAttribute((const void *)g_k1_bulk[N], cudaFuncAttributeMaxDynamicSharedMemorySize, g_k1_bulk_smem[N]);
+                if (e != cudaSuccess) return bp_fail(h, BP_ERR_CUDA, "cudaFuncSetAttribute(%d): %s", g_k1_bulk_smem[N], cudaGetErrorString(e));
+            }
+            g_k1_bulk[N]<<<grid, bthreads, (size_t)g_k1_bulk_smem[N], h->stream>>>(dA, blo, bhi, span, d_partials, d_counter, d_out_dd, xs);
             BP_CHECK_LAUNCH(h);
             BP_CUDA(h, cudaEventRecord(g_const_event[h->device], h->stream));
         }
