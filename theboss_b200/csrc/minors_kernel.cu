@@ -146,7 +146,9 @@ __device__ __forceinline__ void k3_tree_down_real(double w, const double (&cr)[C
 // K3_TERMS_PER_GROUP terms per lane group, at most the launched `chunks`.  Bunched outputs shrink the
 // walk by orders of magnitude, so the grid is sized for the collision-free worst case and blocks beyond
 // `active` exit at once; the finish kernel applies the same rule.
+#ifndef K3_TERMS_PER_GROUP
 #define K3_TERMS_PER_GROUP 192ull
+#endif
 #ifndef K3_PERIODS_PER_GROUP
 #define K3_PERIODS_PER_GROUP 8    // a lane group owns at least this many table periods (group ranges differ by at most one period; 16 -> 8: n = 24 run -0.5 %, n = 16 run -3 %)
 #endif
