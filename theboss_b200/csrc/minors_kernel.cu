@@ -270,6 +270,15 @@ k3_minors_kernel(const double *__restrict__ U0, size_t u_stride, int m, const un
             if (v > 0 && (nxt * K3_PERIODS_PER_GROUP > raw || nxt > (unsigned long long)PMAX)) break;
             P = nxt; a = v;
         }
+        // ... and beyond that while the periods still divide EVENLY among the lane groups (every group the same whole number of
+        // periods: no imbalance to pay for, fewer period boundaries -- a walk of 2^10 terms over 16 groups becomes one 64-term period each)
+        for (int v = a + 1; v < D; ++v) {
+            const unsigned long long nxt = P * (unsigned long long)(item.lim[v] + 1);
+            if (nxt > (unsigned long long)PMAX) break;
+            const unsigned long long np = terms / nxt;
+            if (np < ngroups || np % ngroups) break;
+            P = nxt; a = v;
+        }
         period = (unsigned)P;
         low_digits = a;
     }
